@@ -1,0 +1,119 @@
+"""Product of matrices and scalars.  Mirrors fastmat/Product.pyx.
+
+Nested products are flattened and scalars folded into one factor (fastmat/Product.pyx:90-114); forward applies the
+factors right to left after promoting the input to promote(x, dtype) (:205-221), backward left to right with the
+conjugated scalar (:223-240).
+"""
+import numpy as np
+import torch
+
+from .Matrix import Matrix, cast
+from .core import types as _t
+
+
+def _scalar_type(f):
+    """Smallest fastmat type holding a python / numpy scalar (numpy scalars keep their own dtype)."""
+    if isinstance(f, np.generic):
+        return _t.getFusedType(f.dtype)
+    if isinstance(f, bool):
+        return _t.TYPE_INT8
+    if isinstance(f, int):
+        for t in (np.int8, np.int16, np.int32, np.int64):
+            if np.iinfo(t).min <= f <= np.iinfo(t).max:
+                return _t.getFusedType(t)
+        raise TypeError("Product: integer scalar out of range.")
+    if isinstance(f, float):
+        return _t.TYPE_FLOAT32 if float(np.float32(f)) == f else _t.TYPE_FLOAT64
+    if isinstance(f, complex):
+        return _t.TYPE_COMPLEX64 if complex(np.complex64(f)) == f else _t.TYPE_COMPLEX128
+    raise TypeError("Product: Term is neither scalar nor Matrix.")
+
+
+class Product(Matrix):
+
+    def __init__(self, *matrices, **options):
+        debug = options.get('debug', False)
+        scalar = [1]
+        factors = []
+        ft = [_t.TYPE_INT8]
+
+        def add(items):
+            for f in items:
+                if isinstance(f, torch.Tensor) and f.ndim == 0:
+                    f = f.item()
+                if isinstance(f, np.ndarray) and f.ndim == 0:
+                    f = f[()]
+                if isinstance(f, Matrix):
+                    if isinstance(f, Product):
+                        if f._scalar != 1:
+                            scalar[0] = scalar[0] * f._scalar
+                        add(f.content)
+                    else:
+                        factors.append(f)
+                    ft[0] = _t.promoteTypes(ft[0], f.fusedType)
+                elif np.isscalar(f):
+                    if f != 1:
+                        scalar[0] = scalar[0] * f
+                    ft[0] = _t.promoteTypes(ft[0], _scalar_type(f))
+                else:
+                    raise TypeError("Product: Term is neither scalar nor Matrix.")
+
+        add(matrices)
+        dtype = ft[0]
+        expansion = options.get('typeExpansion', _t.safeTypeExpansion(dtype))
+        if expansion is not None:
+            dtype = _t.promoteTypes(dtype, expansion)
+        if len(factors) < 1:
+            raise ValueError("Product has no terms.")
+        numRows, numCols = factors[0].numRows, factors[0].numCols
+        for ii in range(1, len(factors)):
+            if factors[ii].numRows != numCols:
+                raise ValueError("Product: Dimension mismatch for term %d [%dx%d]" % (ii, numRows, numCols))
+            numCols = factors[ii].numCols
+        self._scalar = np.asarray(scalar[0]).astype(_t.getNumpyType(dtype))[()]     # :143
+        self._content = tuple(factors)
+        self._initProperties(numRows, numCols, dtype, **options)
+        if debug:
+            print("fastmat_b200.Product instance %12x containing:" % (id(self), ))
+            for ii, f in enumerate(factors):
+                print("  [%d]: %s" % (ii, repr(f)))
+
+    def _scale_in(self, x, scalar):
+        ft = _t.promoteTypes(x.dtype, self._fusedType)
+        x = cast(x, ft)
+        if scalar != 1:
+            if _t.isComplex(ft):
+                s = complex(scalar)
+            elif _t.isInteger(ft):
+                s = int(scalar)
+            else:
+                s = float(scalar)
+            x = x * s
+        return x
+
+    def _forward(self, x):
+        r = self._scale_in(x, self._scalar)
+        for f in reversed(self._content):
+            r = f.forward(r)
+        return r
+
+    def _backward(self, x):
+        s = np.conj(self._scalar) if np.iscomplexobj(self._scalar) else self._scalar
+        r = self._scale_in(x, s)
+        for f in self._content:
+            r = f.backward(r)
+        return r
+
+    def _reference(self):
+        arr = None
+        for f in self._content:
+            r = f.reference()
+            r = r.to(_t.getTorchType(_t.promoteTypes(_t.promoteTypes(r.dtype, self._fusedType), _t.TYPE_FLOAT32)))
+            if arr is None:
+                arr = r
+            else:
+                t = torch.promote_types(arr.dtype, r.dtype)
+                arr = arr.to(t) @ r.to(t)
+        if self._scalar != 1:
+            arr = arr * (complex(self._scalar) if np.iscomplexobj(self._scalar) else float(self._scalar))
+        return arr

@@ -1,0 +1,120 @@
+// Complex helpers and small-radix DFT butterflies shared by the FFT / FWHT kernels.
+// Everything is __host__ __device__ so that tests/emul can run the exact kernel index logic on the CPU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define FMB_HD __host__ __device__ __forceinline__
+
+namespace fmb {
+
+template <typename S> struct cplx_of;
+template <> struct cplx_of<float> { typedef float2 type; };
+template <> struct cplx_of<double> { typedef double2 type; };
+template <typename C> struct real_of;
+template <> struct real_of<float2> { typedef float type; };
+template <> struct real_of<double2> { typedef double type; };
+
+template <typename C> FMB_HD C mk(typename real_of<C>::type x, typename real_of<C>::type y) { C r; r.x = x; r.y = y; return r; }
+template <typename C> FMB_HD C cadd(C a, C b) { return mk<C>(a.x + b.x, a.y + b.y); }
+template <typename C> FMB_HD C csub(C a, C b) { return mk<C>(a.x - b.x, a.y - b.y); }
+template <typename C> FMB_HD C cmul(C a, C b) { return mk<C>(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+// a * conj(b)
+template <typename C> FMB_HD C cmulc(C a, C b) { return mk<C>(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }
+template <typename C> FMB_HD C cconj(C a) { return mk<C>(a.x, -a.y); }
+template <typename C> FMB_HD C cmul_mi(C a) { return mk<C>(a.y, -a.x); }   // a * (-i)
+template <typename C> FMB_HD C cmul_pi(C a) { return mk<C>(-a.y, a.x); }   // a * (+i)
+template <typename C> FMB_HD C cscale(C a, typename real_of<C>::type s) { return mk<C>(a.x * s, a.y * s); }
+
+// ---- forward DFTs (kernel e^{-2 pi i rk/P}), in place.  The result X[q] ends up at array position
+// ---- outpos<P>(q) (digit-reversed for the composite radices) so that no register shuffling is needed.
+template <int P> FMB_HD constexpr int outpos(int q) { return q; }
+template <> FMB_HD constexpr int outpos<8>(int q) { return ((q & 3) << 1) | (q >> 2); }     // q = k0 + 4*k1 at 2*k0 + k1
+template <> FMB_HD constexpr int outpos<16>(int q) { return ((q & 3) << 2) | (q >> 2); }    // q = k0 + 4*k1 at 4*k0 + k1
+
+template <typename C> FMB_HD void dft2(C &a, C &b) { C t = a; a = cadd(t, b); b = csub(t, b); }
+
+template <typename C> FMB_HD void dft4(C &v0, C &v1, C &v2, C &v3) {
+    C t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3), t3 = cmul_mi(csub(v1, v3));
+    v0 = cadd(t0, t2); v1 = cadd(t1, t3); v2 = csub(t0, t2); v3 = csub(t1, t3);
+}
+
+template <typename C> FMB_HD void dft3(C &v0, C &v1, C &v2) {
+    typedef typename real_of<C>::type S;
+    const S s = (S)0.86602540378443864676372317075294;
+    C t1 = cadd(v1, v2);
+    C t2 = mk<C>(v0.x - (S)0.5 * t1.x, v0.y - (S)0.5 * t1.y);
+    C t3 = cmul_mi(cscale(csub(v1, v2), s));
+    v0 = cadd(v0, t1); v1 = cadd(t2, t3); v2 = csub(t2, t3);
+}
+
+// radix 8: r = 2*r1 + r0 (r0 in 0..1), q = k0 + 4*k1 (k0 in 0..3, k1 in 0..1):
+//   X[k0 + 4 k1] = sum_{r0} W8^{r0 k0} (-1)^{r0 k1} [ sum_{r1} v[2 r1 + r0] W4^{r1 k0} ]
+template <typename C> FMB_HD void dft8(C *v) {
+    typedef typename real_of<C>::type S;
+    const S h = (S)0.70710678118654752440084436210485;
+    dft4(v[0], v[2], v[4], v[6]);       // y[r0=0][k0] at v[2*k0]
+    dft4(v[1], v[3], v[5], v[7]);       // y[r0=1][k0] at v[2*k0+1]
+    // twiddle y[1][k0] by W8^{k0}
+    C a = v[3]; v[3] = mk<C>((a.x + a.y) * h, (a.y - a.x) * h);            // * (1 - i)/sqrt2
+    v[5] = cmul_mi(v[5]);                                                   // * -i
+    a = v[7]; v[7] = mk<C>((a.y - a.x) * h, -(a.x + a.y) * h);             // * (-1 - i)/sqrt2
+    dft2(v[0], v[1]); dft2(v[2], v[3]); dft2(v[4], v[5]); dft2(v[6], v[7]); // X[k0 + 4 k1] at v[2*k0 + k1]
+}
+
+// radix 16: r = 4*r1 + r0, q = k0 + 4*k1; X[k0 + 4 k1] = sum_{r0} W16^{r0 k0} W4^{r0 k1} [sum_{r1} v[4 r1 + r0] W4^{r1 k0}]
+template <typename C> FMB_HD void dft16(C *v) {
+    typedef typename real_of<C>::type S;
+    const S h = (S)0.70710678118654752440084436210485;
+    const S c1 = (S)0.92387953251128675612818318939679;   // cos(pi/8)
+    const S s1 = (S)0.38268343236508977172845998403040;   // sin(pi/8)
+#pragma unroll
+    for (int r0 = 0; r0 < 4; ++r0) dft4(v[r0], v[4 + r0], v[8 + r0], v[12 + r0]);   // y[r0][k0] at v[4*k0 + r0]
+    // twiddles W16^{r0*k0} on v[4*k0 + r0]
+    C a;
+    // k0 = 1: W^1, W^2, W^3
+    a = v[5];  v[5]  = mk<C>(a.x * c1 + a.y * s1, a.y * c1 - a.x * s1);               // W16^1 = c1 - i s1
+    a = v[6];  v[6]  = mk<C>((a.x + a.y) * h, (a.y - a.x) * h);                       // W16^2 = (1 - i)/sqrt2
+    a = v[7];  v[7]  = mk<C>(a.x * s1 + a.y * c1, a.y * s1 - a.x * c1);               // W16^3 = s1 - i c1
+    // k0 = 2: W^2, W^4, W^6
+    a = v[9];  v[9]  = mk<C>((a.x + a.y) * h, (a.y - a.x) * h);
+    v[10] = cmul_mi(v[10]);                                                           // W16^4 = -i
+    a = v[11]; v[11] = mk<C>((a.y - a.x) * h, -(a.x + a.y) * h);                      // W16^6 = (-1 - i)/sqrt2
+    // k0 = 3: W^3, W^6, W^9
+    a = v[13]; v[13] = mk<C>(a.x * s1 + a.y * c1, a.y * s1 - a.x * c1);               // W16^3
+    a = v[14]; v[14] = mk<C>((a.y - a.x) * h, -(a.x + a.y) * h);                      // W16^6
+    a = v[15]; v[15] = mk<C>(-a.x * c1 - a.y * s1, a.x * s1 - a.y * c1);              // W16^9 = -c1 + i s1
+#pragma unroll
+    for (int k0 = 0; k0 < 4; ++k0) dft4(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]);
+}
+
+// generic odd prime radix, constants taken from the unit-root table of the transform (wp[r] = e^{-2 pi i r/P})
+template <typename C, int P> FMB_HD void dft_odd(C *v, const C *wp /* wp[1..(P-1)/2] valid */) {
+    typedef typename real_of<C>::type S;
+    constexpr int H = (P - 1) / 2;
+    C a[H + 1], b[H + 1];
+#pragma unroll
+    for (int r = 1; r <= H; ++r) { a[r] = cadd(v[r], v[P - r]); b[r] = csub(v[r], v[P - r]); }
+    C x0 = v[0];
+    C sum = x0;
+#pragma unroll
+    for (int r = 1; r <= H; ++r) sum = cadd(sum, a[r]);
+    v[0] = sum;
+#pragma unroll
+    for (int q = 1; q <= H; ++q) {
+        S ar = x0.x, ai = x0.y, br = 0, bi = 0;
+#pragma unroll
+        for (int r = 1; r <= H; ++r) {
+            int e = (r * q) % P;
+            // W^{e} = cos - i sin; use symmetry W^{P-e} = conj(W^{e})
+            S c = (e <= H) ? wp[e].x : wp[P - e].x;
+            S s = (e <= H) ? -wp[e].y : wp[P - e].y;       // s = sin(2 pi e / P)
+            ar += c * a[r].x; ai += c * a[r].y;
+            br += s * b[r].y; bi -= s * b[r].x;             // (-i s) * b = (s b.y, -s b.x)
+        }
+        v[q] = mk<C>(ar + br, ai + bi);
+        v[P - q] = mk<C>(ar - br, ai - bi);
+    }
+}
+
+}  // namespace fmb

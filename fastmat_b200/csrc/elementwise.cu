@@ -1,0 +1,243 @@
+// Exact element-wise pieces of the apply path: Diag multiply (fastmat/Diag.pyx:149-167 ->
+// fastmat/core/cmath.pyx:958-1012 _multiply), the Partial gather / scatter (fastmat/Partial.pyx:268-294),
+// complex conjugate (fastmat/core/cmath.pyx:744-840).  All are pure bandwidth: one read, one write.
+#include "common.h"
+#include "cx.cuh"
+
+namespace fmb {
+
+struct EwParams {
+    long long n, M;
+    const void *x; long long xrs, xcs;
+    void *y; long long yrs, ycs;
+    const void *d;           // diag vector / index vector
+    int dt_x, dt_d;
+    int conj_d;
+    int c_fastest;           // 1: consecutive threads walk columns (row-major arrays)
+};
+
+// ---- typed load with conversion to the output type ------------------------------------------------------
+template <typename O> struct Conv;
+template <typename O> FMB_HD O from_real_i(long long v) { return (O)v; }
+template <typename O> FMB_HD O from_real_f(double v) { return (O)v; }
+
+template <typename O, bool CPLX> struct Loader {
+    // real output types
+    static FMB_HD O load(const void *p, int dt, long long i) {
+        switch (dt) {
+            case FMB_INT8: return (O)((const int8_t *)p)[i];
+            case FMB_INT16: return (O)((const int16_t *)p)[i];
+            case FMB_INT32: return (O)((const int32_t *)p)[i];
+            case FMB_INT64: return (O)((const int64_t *)p)[i];
+            case FMB_FLOAT32: return (O)((const float *)p)[i];
+            case FMB_FLOAT64: return (O)((const double *)p)[i];
+            default: return (O)0;
+        }
+    }
+};
+template <typename O> struct Loader<O, true> {
+    typedef typename real_of<O>::type S;
+    static FMB_HD O load(const void *p, int dt, long long i) {
+        switch (dt) {
+            case FMB_INT8: return mk<O>((S)((const int8_t *)p)[i], 0);
+            case FMB_INT16: return mk<O>((S)((const int16_t *)p)[i], 0);
+            case FMB_INT32: return mk<O>((S)((const int32_t *)p)[i], 0);
+            case FMB_INT64: return mk<O>((S)((const int64_t *)p)[i], 0);
+            case FMB_FLOAT32: return mk<O>((S)((const float *)p)[i], 0);
+            case FMB_FLOAT64: return mk<O>((S)((const double *)p)[i], 0);
+            case FMB_COMPLEX64: { float2 v = ((const float2 *)p)[i]; return mk<O>((S)v.x, (S)v.y); }
+            case FMB_COMPLEX128: { double2 v = ((const double2 *)p)[i]; return mk<O>((S)v.x, (S)v.y); }
+            default: return mk<O>(0, 0);
+        }
+    }
+};
+
+template <typename O> struct Mul { static FMB_HD O mul(O a, O b, int) { return a * b; } };
+template <> struct Mul<int8_t> { static FMB_HD int8_t mul(int8_t a, int8_t b, int) { return (int8_t)(uint8_t)((unsigned)(uint8_t)a * (unsigned)(uint8_t)b); } };
+template <> struct Mul<int16_t> { static FMB_HD int16_t mul(int16_t a, int16_t b, int) { return (int16_t)(uint16_t)((unsigned)(uint16_t)a * (unsigned)(uint16_t)b); } };
+template <> struct Mul<int32_t> { static FMB_HD int32_t mul(int32_t a, int32_t b, int) { return (int32_t)((uint32_t)a * (uint32_t)b); } };
+template <> struct Mul<int64_t> { static FMB_HD int64_t mul(int64_t a, int64_t b, int) { return (int64_t)((uint64_t)a * (uint64_t)b); } };
+template <> struct Mul<float2> { static FMB_HD float2 mul(float2 a, float2 b, int cj) { return cj ? cmulc(a, b) : cmul(a, b); } };
+template <> struct Mul<double2> { static FMB_HD double2 mul(double2 a, double2 b, int cj) { return cj ? cmulc(a, b) : cmul(a, b); } };
+
+FMB_HD void ew_decode(const EwParams &p, long long e, long long &n, long long &c) {
+    if (p.c_fastest) { n = e / p.M; c = e - n * p.M; }
+    else { c = e / p.n; n = e - c * p.n; }
+}
+
+template <typename O, bool CPLX> __global__ void __launch_bounds__(256) diag_kernel(const __grid_constant__ EwParams p) {
+    const long long total = p.n * p.M;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long n, c;
+        ew_decode(p, e, n, c);
+        O xv = Loader<O, CPLX>::load(p.x, p.dt_x, n * p.xrs + c * p.xcs);
+        O dv = Loader<O, CPLX>::load(p.d, p.dt_d, n);
+        ((O *)p.y)[n * p.yrs + c * p.ycs] = Mul<O>::mul(xv, dv, p.conj_d);
+    }
+}
+
+template <typename B> __global__ void __launch_bounds__(256) gather_kernel(const __grid_constant__ EwParams p) {
+    // y[r, c] = x[idx[r], c], r < n
+    const long long total = p.n * p.M;
+    const long long *idx = (const long long *)p.d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long r, c;
+        ew_decode(p, e, r, c);
+        ((B *)p.y)[r * p.yrs + c * p.ycs] = ((const B *)p.x)[__ldg(idx + r) * p.xrs + c * p.xcs];
+    }
+}
+
+template <typename B> __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ EwParams p) {
+    // y[idx[r], c] = x[r, c], r < n   (y zero-filled beforehand)
+    const long long total = p.n * p.M;
+    const long long *idx = (const long long *)p.d;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long r, c;
+        ew_decode(p, e, r, c);
+        ((B *)p.y)[__ldg(idx + r) * p.yrs + c * p.ycs] = ((const B *)p.x)[r * p.xrs + c * p.xcs];
+    }
+}
+
+template <typename B> __global__ void __launch_bounds__(256) zero_kernel(const __grid_constant__ EwParams p) {
+    const long long total = p.n * p.M;
+    B z;
+    memset(&z, 0, sizeof(B));
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long r, c;
+        ew_decode(p, e, r, c);
+        ((B *)p.y)[r * p.yrs + c * p.ycs] = z;
+    }
+}
+
+template <typename C> __global__ void __launch_bounds__(256) conj_kernel(const __grid_constant__ EwParams p) {
+    const long long total = p.n * p.M;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long r, c;
+        ew_decode(p, e, r, c);
+        C v = ((const C *)p.x)[r * p.xrs + c * p.xcs];
+        v.y = -v.y;
+        ((C *)p.y)[r * p.yrs + c * p.ycs] = v;
+    }
+}
+
+static unsigned ew_grid(long long total) {
+    long long blocks = (total + 255) / 256;
+    long long cap = (long long)device_props().sm_count * 16;        // grid-stride: a multiple of the SM count
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (unsigned)blocks;
+}
+
+static EwParams ew_params(int64_t n, int64_t M, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs) {
+    EwParams p;
+    memset(&p, 0, sizeof(p));
+    p.n = n; p.M = M; p.x = x; p.xrs = xrs; p.xcs = xcs; p.y = y; p.yrs = yrs; p.ycs = ycs;
+    p.c_fastest = (ycs == 1 && M > 1) ? 1 : 0;
+    return p;
+}
+
+#ifdef FMB_EMULATE
+#define FMB_EW_LAUNCH(kernel, p, st) do { set_error("element-wise kernels are not emulated"); return FMB_ERR_NOTIMPL; } while (0)
+#else
+#define FMB_EW_LAUNCH(kernel, p, st)                                           \
+    do {                                                                       \
+        if ((p).n * (p).M > 0) {                                               \
+            kernel<<<ew_grid((p).n * (p).M), 256, 0, st>>>(p);                 \
+            FMB_LAUNCH_OK();                                                   \
+        }                                                                      \
+    } while (0)
+#endif
+
+int diag_apply(const void *d_dev, int dt_d, int64_t n, int conj_d, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
+               int64_t ycs, int64_t M, int dt_x, int dt_out, cudaStream_t st) {
+    EwParams p = ew_params(n, M, x, xrs, xcs, y, yrs, ycs);
+    p.d = d_dev; p.dt_x = dt_x; p.dt_d = dt_d; p.conj_d = conj_d;
+    const bool in_cplx = dt_x >= FMB_COMPLEX64 || dt_d >= FMB_COMPLEX64;
+    if (in_cplx && dt_out < FMB_COMPLEX64) { set_error("Diag: complex operands need a complex output"); return FMB_ERR_TYPE; }
+    switch (dt_out) {
+        case FMB_INT8: FMB_EW_LAUNCH((diag_kernel<int8_t, false>), p, st); break;
+        case FMB_INT16: FMB_EW_LAUNCH((diag_kernel<int16_t, false>), p, st); break;
+        case FMB_INT32: FMB_EW_LAUNCH((diag_kernel<int32_t, false>), p, st); break;
+        case FMB_INT64: FMB_EW_LAUNCH((diag_kernel<int64_t, false>), p, st); break;
+        case FMB_FLOAT32: FMB_EW_LAUNCH((diag_kernel<float, false>), p, st); break;
+        case FMB_FLOAT64: FMB_EW_LAUNCH((diag_kernel<double, false>), p, st); break;
+        case FMB_COMPLEX64: FMB_EW_LAUNCH((diag_kernel<float2, true>), p, st); break;
+        case FMB_COMPLEX128: FMB_EW_LAUNCH((diag_kernel<double2, true>), p, st); break;
+        default: set_error("Diag: unsupported output dtype %d", dt_out); return FMB_ERR_TYPE;
+    }
+    return FMB_OK;
+}
+
+template <template <typename> class K> struct BySize {};
+
+int gather_apply(const void *idx_dev, int64_t nsel, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs,
+                 int64_t M, int dtype, cudaStream_t st) {
+    EwParams p = ew_params(nsel, M, x, xrs, xcs, y, yrs, ycs);
+    p.d = idx_dev;
+    switch (dtype_size(dtype)) {
+        case 1: FMB_EW_LAUNCH(gather_kernel<uint8_t>, p, st); break;
+        case 2: FMB_EW_LAUNCH(gather_kernel<uint16_t>, p, st); break;
+        case 4: FMB_EW_LAUNCH(gather_kernel<uint32_t>, p, st); break;
+        case 8: FMB_EW_LAUNCH(gather_kernel<uint64_t>, p, st); break;
+        case 16: FMB_EW_LAUNCH(gather_kernel<double2>, p, st); break;
+        default: set_error("Partial: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
+    }
+    return FMB_OK;
+}
+
+int scatter_apply(const void *idx_dev, int64_t nsel, int64_t ntotal, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
+                  int64_t ycs, int64_t M, int dtype, cudaStream_t st) {
+    EwParams z = ew_params(ntotal, M, nullptr, 0, 0, y, yrs, ycs);
+    EwParams p = ew_params(nsel, M, x, xrs, xcs, y, yrs, ycs);
+    p.d = idx_dev;
+    switch (dtype_size(dtype)) {
+        case 1: FMB_EW_LAUNCH(zero_kernel<uint8_t>, z, st); FMB_EW_LAUNCH(scatter_kernel<uint8_t>, p, st); break;
+        case 2: FMB_EW_LAUNCH(zero_kernel<uint16_t>, z, st); FMB_EW_LAUNCH(scatter_kernel<uint16_t>, p, st); break;
+        case 4: FMB_EW_LAUNCH(zero_kernel<uint32_t>, z, st); FMB_EW_LAUNCH(scatter_kernel<uint32_t>, p, st); break;
+        case 8: FMB_EW_LAUNCH(zero_kernel<uint64_t>, z, st); FMB_EW_LAUNCH(scatter_kernel<uint64_t>, p, st); break;
+        case 16: FMB_EW_LAUNCH(zero_kernel<double2>, z, st); FMB_EW_LAUNCH(scatter_kernel<double2>, p, st); break;
+        default: set_error("Partial: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
+    }
+    return FMB_OK;
+}
+
+int conj_apply(const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t n, int64_t M, int dtype, cudaStream_t st) {
+    EwParams p = ew_params(n, M, x, xrs, xcs, y, yrs, ycs);
+    if (dtype == FMB_COMPLEX64) { FMB_EW_LAUNCH(conj_kernel<float2>, p, st); return FMB_OK; }
+    if (dtype == FMB_COMPLEX128) { FMB_EW_LAUNCH(conj_kernel<double2>, p, st); return FMB_OK; }
+    // real types: conj is the identity -> plain strided copy through the gather kernel with the identity index
+    set_error("conjugate of a real array is the array itself; the caller should not copy");
+    return FMB_ERR_TYPE;
+}
+
+// copy / cast (x of dt_in) -> (y of dt_out) through the Diag kernel's converting loader with d == 1 is wasteful;
+// a dedicated cast: y = (O) x
+template <typename O, bool CPLX> __global__ void __launch_bounds__(256) cast_kernel(const __grid_constant__ EwParams p) {
+    const long long total = p.n * p.M;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long n, c;
+        ew_decode(p, e, n, c);
+        ((O *)p.y)[n * p.yrs + c * p.ycs] = Loader<O, CPLX>::load(p.x, p.dt_x, n * p.xrs + c * p.xcs);
+    }
+}
+
+int cast_apply(const void *x, int64_t xrs, int64_t xcs, int dt_x, void *y, int64_t yrs, int64_t ycs, int dt_out, int64_t n, int64_t M,
+               cudaStream_t st) {
+    EwParams p = ew_params(n, M, x, xrs, xcs, y, yrs, ycs);
+    p.dt_x = dt_x;
+    if (dt_x >= FMB_COMPLEX64 && dt_out < FMB_COMPLEX64) { set_error("cast: complex -> real is not allowed"); return FMB_ERR_TYPE; }
+    switch (dt_out) {
+        case FMB_INT8: FMB_EW_LAUNCH((cast_kernel<int8_t, false>), p, st); break;
+        case FMB_INT16: FMB_EW_LAUNCH((cast_kernel<int16_t, false>), p, st); break;
+        case FMB_INT32: FMB_EW_LAUNCH((cast_kernel<int32_t, false>), p, st); break;
+        case FMB_INT64: FMB_EW_LAUNCH((cast_kernel<int64_t, false>), p, st); break;
+        case FMB_FLOAT32: FMB_EW_LAUNCH((cast_kernel<float, false>), p, st); break;
+        case FMB_FLOAT64: FMB_EW_LAUNCH((cast_kernel<double, false>), p, st); break;
+        case FMB_COMPLEX64: FMB_EW_LAUNCH((cast_kernel<float2, true>), p, st); break;
+        case FMB_COMPLEX128: FMB_EW_LAUNCH((cast_kernel<double2, true>), p, st); break;
+        default: set_error("cast: unsupported output dtype %d", dt_out); return FMB_ERR_TYPE;
+    }
+    return FMB_OK;
+}
+
+}  // namespace fmb

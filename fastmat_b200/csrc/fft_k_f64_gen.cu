@@ -1,0 +1,6 @@
+#include "fft_kernel_inst.cuh"
+namespace fmb {
+int launch_fft_f64_gen(const PassParams<double2> &p, unsigned tiles, int nt, size_t smem, cudaStream_t st) {
+    return launch_fft_kernel_impl<double2, false>(p, tiles, nt, smem, st);
+}
+}  // namespace fmb

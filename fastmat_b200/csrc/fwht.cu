@@ -1,0 +1,287 @@
+// Fast Walsh-Hadamard transform (natural / Sylvester order, unnormalised) for all eight fastmat dtypes.
+//
+// Reference: fastmat/Hadamard.pyx:164-230 (_forwardC) applies, per column, `order` in-place radix-2 sweeps with
+// butterfly distance 1, 2, 4, ... and the butterfly (a, b) -> (a + b, a - b) of _hadamardCore (:36-61) in the
+// array's own dtype.  Here a column is processed in one or more shared-memory passes; pass p covers a contiguous
+// range of index bits [s, s+b) and inside a pass the bits are taken in ASCENDING order, so the sequence of
+// additions every output element sees is exactly the reference's: integer results are bit-exact by ring
+// arithmetic, and floating-point results are bit-exact too because the rounding sequence is identical.
+//
+// Per pass one CTA owns a tile [2^b "mid" values] x [T lines]; a line is a (column, low-bits) pair for the
+// column-major layout, or a column for the row-major layout, so that the contiguous memory direction is always
+// the one consecutive threads walk.  Passes after the first run in place on the output; the host drives them
+// slab-of-columns by slab so that the slab is still L2-resident when the next pass reads it.
+#include "common.h"
+#include "cx.cuh"
+
+namespace fmb {
+
+template <typename T> struct HOps {
+    static FMB_HD T add(T a, T b) { return a + b; }
+    static FMB_HD T sub(T a, T b) { return a - b; }
+};
+template <> struct HOps<int8_t> {
+    static FMB_HD int8_t add(int8_t a, int8_t b) { return (int8_t)(uint8_t)((unsigned)(uint8_t)a + (unsigned)(uint8_t)b); }
+    static FMB_HD int8_t sub(int8_t a, int8_t b) { return (int8_t)(uint8_t)((unsigned)(uint8_t)a - (unsigned)(uint8_t)b); }
+};
+template <> struct HOps<int16_t> {
+    static FMB_HD int16_t add(int16_t a, int16_t b) { return (int16_t)(uint16_t)((unsigned)(uint16_t)a + (unsigned)(uint16_t)b); }
+    static FMB_HD int16_t sub(int16_t a, int16_t b) { return (int16_t)(uint16_t)((unsigned)(uint16_t)a - (unsigned)(uint16_t)b); }
+};
+template <> struct HOps<int32_t> {
+    static FMB_HD int32_t add(int32_t a, int32_t b) { return (int32_t)((uint32_t)a + (uint32_t)b); }
+    static FMB_HD int32_t sub(int32_t a, int32_t b) { return (int32_t)((uint32_t)a - (uint32_t)b); }
+};
+template <> struct HOps<int64_t> {
+    static FMB_HD int64_t add(int64_t a, int64_t b) { return (int64_t)((uint64_t)a + (uint64_t)b); }
+    static FMB_HD int64_t sub(int64_t a, int64_t b) { return (int64_t)((uint64_t)a - (uint64_t)b); }
+};
+template <> struct HOps<float2> {
+    static FMB_HD float2 add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+    static FMB_HD float2 sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+};
+template <> struct HOps<double2> {
+    static FMB_HD double2 add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+    static FMB_HD double2 sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+};
+
+struct FwhtPass {
+    int b;                    // bits handled by this pass
+    int s;                    // lowest bit handled
+    int T;                    // lines per tile
+    int mid_contig;           // 1: the mid index is the contiguous memory direction (column-major, s == 0)
+    int pad;                  // shared-memory padding: index e -> e + (e >> 4) when set
+    long long lines_total;    // number of lines
+    long long lo_count;       // 2^s (column-major) or 1 (row-major: lines are columns)
+    long long hi_count;       // 2^(order - s - b)
+    long long ncols;
+    int row_major;            // line decode: 0: line = (c*hi_count + hi)*lo_count + lo ; 1: line = (hi*lo_count + lo)*ncols + c
+    const void *in;
+    void *out;
+    long long in_rs, in_cs, out_rs, out_cs;
+};
+
+template <typename T> FMB_HD void fwht_line_base(const FwhtPass &p, long long line, long long &in_off, long long &out_off) {
+    long long c, hi, lo;
+    if (p.row_major) {
+        long long q = line / p.ncols;
+        c = line - q * p.ncols;
+        hi = q / p.lo_count;
+        lo = q - hi * p.lo_count;
+    } else {
+        lo = line % p.lo_count;
+        long long q = line / p.lo_count;
+        c = q / p.hi_count;
+        hi = q - c * p.hi_count;
+    }
+    long long n = (hi << (p.s + p.b)) | lo;
+    in_off = c * p.in_cs + n * p.in_rs;
+    out_off = c * p.out_cs + n * p.out_rs;
+}
+
+template <typename T, int KK> FMB_HD void fwht_substage(T *sm, int u, int b, int T_, int pad, int tid, int NT) {
+    constexpr int E = 1 << KK;
+    const int groups = (1 << (b - KK)) * T_;
+    for (int g = tid; g < groups; g += NT) {
+        int l = g % T_;
+        int mg = g / T_;
+        int mid_base = ((mg >> u) << (u + KK)) | (mg & ((1 << u) - 1));
+        T v[E];
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            int e = (mid_base + (r << u)) * T_ + l;
+            v[r] = sm[pad ? e + (e >> 4) : e];
+        }
+#pragma unroll
+        for (int lev = 0; lev < KK; ++lev) {          // ascending bit order inside the sub-stage
+            const int d = 1 << lev;
+#pragma unroll
+            for (int r = 0; r < E; ++r) {
+                if ((r & d) == 0) {
+                    T a = v[r], bb = v[r | d];
+                    v[r] = HOps<T>::add(a, bb);
+                    v[r | d] = HOps<T>::sub(a, bb);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < E; ++r) {
+            int e = (mid_base + (r << u)) * T_ + l;
+            sm[pad ? e + (e >> 4) : e] = v[r];
+        }
+    }
+}
+
+template <typename T, typename Sync>
+FMB_HD void fwht_pass_body(const FwhtPass &p, long long tile, int tid, int NT, T *sm, Sync &sync) {
+    const int nmid = 1 << p.b;
+    const int telems = nmid * p.T;
+    const long long step_in = ((long long)1 << p.s) * p.in_rs, step_out = ((long long)1 << p.s) * p.out_rs;
+    // ---- load tile (memory order)
+    for (int e = tid; e < telems; e += NT) {
+        int mid, t;
+        if (p.mid_contig) { t = e / nmid; mid = e - t * nmid; }
+        else { mid = e / p.T; t = e - mid * p.T; }
+        long long line = tile * p.T + t;
+        if (line < p.lines_total) {
+            long long io, oo;
+            fwht_line_base<T>(p, line, io, oo);
+            int se = mid * p.T + t;
+            sm[p.pad ? se + (se >> 4) : se] = ((const T *)p.in)[io + (long long)mid * step_in];
+        }
+    }
+    sync();
+    // ---- butterflies, ascending bit order, up to 4 bits per sub-stage
+    for (int u = 0; u < p.b;) {
+        int kk = p.b - u;
+        if (kk > 4) kk = 4;
+        switch (kk) {
+            case 4: fwht_substage<T, 4>(sm, u, p.b, p.T, p.pad, tid, NT); break;
+            case 3: fwht_substage<T, 3>(sm, u, p.b, p.T, p.pad, tid, NT); break;
+            case 2: fwht_substage<T, 2>(sm, u, p.b, p.T, p.pad, tid, NT); break;
+            default: fwht_substage<T, 1>(sm, u, p.b, p.T, p.pad, tid, NT); break;
+        }
+        u += kk;
+        sync();
+    }
+    // ---- store tile
+    for (int e = tid; e < telems; e += NT) {
+        int mid, t;
+        if (p.mid_contig) { t = e / nmid; mid = e - t * nmid; }
+        else { mid = e / p.T; t = e - mid * p.T; }
+        long long line = tile * p.T + t;
+        if (line < p.lines_total) {
+            long long io, oo;
+            fwht_line_base<T>(p, line, io, oo);
+            int se = mid * p.T + t;
+            ((T *)p.out)[oo + (long long)mid * step_out] = sm[p.pad ? se + (se >> 4) : se];
+        }
+    }
+}
+
+struct FwhtDevSync {
+    FMB_HD void operator()() const {
+#ifdef __CUDA_ARCH__
+        __syncthreads();
+#endif
+    }
+};
+
+template <typename T> __global__ void __launch_bounds__(256) fwht_pass_kernel(const __grid_constant__ FwhtPass p) {
+    extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
+    FwhtDevSync sync;
+    fwht_pass_body<T, FwhtDevSync>(p, (long long)blockIdx.x, (int)threadIdx.x, (int)blockDim.x, reinterpret_cast<T *>(fwht_smem_raw), sync);
+}
+
+template <typename T> static int launch_fwht_pass(const FwhtPass &p, cudaStream_t st) {
+    const int nmid = 1 << p.b;
+    size_t elems = (size_t)nmid * p.T;
+    size_t smem = (elems + (p.pad ? (elems >> 4) + 1 : 0)) * sizeof(T);
+    long long tiles = (p.lines_total + p.T - 1) / p.T;
+    if (tiles <= 0) return FMB_OK;
+    if (tiles > 2147483647LL) { set_error("FWHT: too many tiles"); return FMB_ERR_VALUE; }
+#ifdef FMB_EMULATE
+    emulate_launch(tiles, 64, smem, [&](long long tile, int tid, int nt, void *sm, const std::function<void()> &bar) {
+        struct S { const std::function<void()> &b; void operator()() const { b(); } } sync{bar};
+        fwht_pass_body<T, S>(p, tile, tid, nt, (T *)sm, sync);
+    });
+    g_launches.fetch_add(1);
+    return FMB_OK;
+#else
+    static int attr_done = 0;
+    if (!attr_done) {
+        FMB_CUDA_OK(cudaFuncSetAttribute(fwht_pass_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
+        attr_done = 1;
+    }
+    fwht_pass_kernel<T><<<(unsigned)tiles, 256, smem, st>>>(p);
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+#endif
+}
+
+template <typename T>
+static int fwht_typed(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, cudaStream_t st) {
+    const bool row_major = (xcs == 1 && M > 1);
+    // ---- split the bits into passes
+    const int tile_bytes = 64 << 10;
+    std::vector<int> bits;
+    int remaining = order;
+    int max_strided_T = (sizeof(T) >= 8) ? 16 : 32;
+    int bmax_strided = 0;
+    while (((size_t)1 << (bmax_strided + 1)) * max_strided_T * sizeof(T) <= (size_t)tile_bytes && bmax_strided < 10) ++bmax_strided;
+    if (!row_major) {
+        int b0max = 0;
+        while (((size_t)1 << (b0max + 1)) * sizeof(T) <= (size_t)(tile_bytes / 2) && b0max < 12) ++b0max;
+        int b0 = std::min(order, b0max);
+        bits.push_back(b0);
+        remaining -= b0;
+    }
+    if (remaining > 0) {
+        int npass = (remaining + bmax_strided - 1) / bmax_strided;
+        int base = remaining / npass, extra = remaining % npass;
+        for (int i = 0; i < npass; ++i) bits.push_back(base + (i < extra ? 1 : 0));
+    }
+    // ---- slab of columns that stays L2-resident between passes
+    size_t l2 = device_props().l2_bytes ? device_props().l2_bytes : (size_t)100 << 20;
+    int64_t slab = (int64_t)((l2 / 3) / (((size_t)1 << order) * sizeof(T)));
+    if (slab < 1) slab = 1;
+    if (bits.size() == 1) slab = M;
+    for (int64_t c0 = 0; c0 < M; c0 += slab) {
+        const int64_t nc = std::min<int64_t>(slab, M - c0);
+        int s = 0;
+        for (size_t pi = 0; pi < bits.size(); ++pi) {
+            FwhtPass p;
+            memset(&p, 0, sizeof(p));
+            p.b = bits[pi]; p.s = s;
+            p.row_major = row_major;
+            p.ncols = nc;
+            p.hi_count = (long long)1 << (order - s - p.b);
+            if (row_major) {
+                p.lo_count = (long long)1 << s;
+                p.mid_contig = 0;
+                p.T = max_strided_T;
+                p.lines_total = nc * p.lo_count * p.hi_count;
+                p.pad = 0;
+            } else if (s == 0) {
+                p.lo_count = 1;
+                p.mid_contig = 1;
+                p.T = 1;
+                // small transforms: several columns / chunks per CTA so that a CTA has >= 2048 elements of work
+                while (((long long)p.T << p.b) < 2048 && p.T < 256) p.T *= 2;
+                p.lines_total = nc * p.hi_count;
+                p.pad = 1;
+            } else {
+                p.lo_count = (long long)1 << s;
+                p.mid_contig = 0;
+                p.T = (int)std::min<long long>(max_strided_T, p.lo_count);
+                p.lines_total = nc * p.lo_count * p.hi_count;
+                p.pad = (p.T < 32) ? 1 : 0;
+            }
+            const bool first = (pi == 0);
+            p.in = first ? (const char *)x + (size_t)(c0 * xcs) * sizeof(T) : (const char *)y + (size_t)(c0 * ycs) * sizeof(T);
+            p.in_rs = first ? xrs : yrs; p.in_cs = first ? xcs : ycs;
+            p.out = (char *)y + (size_t)(c0 * ycs) * sizeof(T);
+            p.out_rs = yrs; p.out_cs = ycs;
+            int rc = launch_fwht_pass<T>(p, st);
+            if (rc) return rc;
+            s += p.b;
+        }
+    }
+    return FMB_OK;
+}
+
+int fwht_apply(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dtype, cudaStream_t st) {
+    switch (dtype) {
+        case FMB_INT8: return fwht_typed<int8_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_INT16: return fwht_typed<int16_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_INT32: return fwht_typed<int32_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_INT64: return fwht_typed<int64_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_FLOAT32: return fwht_typed<float>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_FLOAT64: return fwht_typed<double>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_COMPLEX64: return fwht_typed<float2>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_COMPLEX128: return fwht_typed<double2>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        default: set_error("Hadamard: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
+    }
+}
+
+}  // namespace fmb

@@ -1,0 +1,497 @@
+"""GPU parity tests: the CUDA path, called through the class layer -> C-ABI (libfastmat_b200.so), against
+(a) the fixtures frozen from the real reference (tests/golden) and (b) the numpy oracle on seeded inputs, plus
+size-independent properties at the BASELINE sizes.
+
+Tolerance (BASELINE.json north_star): max|y - y_ref| <= tol * ||x||_2 * log2(N) per column with tol = 1e-5 for
+complex64/float32 and 1e-12 for complex128/float64; integer Hadamard / Permutation / Partial are bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_data, seeded, seeded_typed
+
+pytestmark = pytest.mark.gpu
+
+G = golden_data()
+TOL64, TOL128 = 1e-5, 1e-12
+
+
+@pytest.fixture(scope='module')
+def fm():
+    import fastmat_b200
+    assert torch.cuda.is_available()
+    return fastmat_b200
+
+
+@pytest.fixture(scope='module')
+def orc():
+    from oracle import fastmat_oracle
+    return fastmat_oracle
+
+
+def dev(a, layout='F'):
+    """numpy (n, M) / (n,) -> CUDA tensor in column-major ('F', fastmat native) or row-major ('C') layout."""
+    a = np.asarray(a)
+    if a.ndim == 1:
+        return torch.from_numpy(a.copy()).cuda()
+    if layout == 'C':
+        return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def nerr(y, ref, x, n):
+    """Error normalised by ||x|| log2 N (per column, worst column)."""
+    y, ref, x = np.asarray(y), np.asarray(ref), np.asarray(x)
+    if y.ndim == 1:
+        y, ref, x = y[:, None], ref[:, None], x[:, None]
+    nx = np.linalg.norm(x.astype(np.complex128), axis=0)
+    nx[nx == 0] = 1.0
+    return float((np.abs(y - ref).max(axis=0) / (nx * max(1.0, np.log2(max(n, 2))))).max())
+
+
+def check_pair(M, x, ref_f, y, ref_b, n, both_precisions=True, layouts=('F', 'C')):
+    """forward(x) ~ ref_f and backward(y) ~ ref_b in complex128 and (cast) complex64, both layouts."""
+    for lay in layouts:
+        f = M.forward(dev(x, lay))
+        b = M.backward(dev(y, lay))
+        assert f.dtype == torch.complex128 and b.dtype == torch.complex128
+        assert nerr(host(f), ref_f, x, n) < TOL128, ('fwd c128', lay)
+        assert nerr(host(b), ref_b, y, n) < TOL128, ('bwd c128', lay)
+        if both_precisions:
+            x32, y32 = x.astype(np.complex64), y.astype(np.complex64)
+            f = M.forward(dev(x32, lay))
+            b = M.backward(dev(y32, lay))
+            assert nerr(host(f), ref_f, x, n) < TOL64, ('fwd c64', lay)
+            assert nerr(host(b), ref_b, y, n) < TOL64, ('bwd c64', lay)
+
+
+# ------------------------------------------------------------------------------------------- Fourier
+@pytest.mark.parametrize('name', G.cases('fourier'))
+def test_fourier_golden(fm, name):
+    p = G.params(name)
+    x = G.get(name, 'x')
+    F = fm.Fourier(p['n'], optimize=p['optimize'])
+    check_pair(F, x, G.get(name, 'fwd'), x, G.get(name, 'bwd'), p['n'], layouts=('F', 'C') if x.ndim == 2 else ('F', ))
+    out = F.forward(dev(x.astype(np.complex64)))
+    assert out.dtype == torch.complex64 and out.ndim == x.ndim
+
+
+@pytest.mark.parametrize('name', G.cases('fourier_big'))
+def test_fourier_big_golden(fm, name):
+    p = G.params(name)
+    n = p['n']
+    x = seeded(p['seed'], n, p['cols'])
+    F = fm.Fourier(n, optimize=p['optimize'])
+    assert F._numL == p['numL']                       # the reference's Bluestein decision is reproduced
+    for lay in ('F', 'C'):
+        for dt, tol in ((np.complex128, TOL128), (np.complex64, TOL64)):
+            xd = dev(x.astype(dt), lay)
+            keep = xd.clone()
+            for d, y in (('fwd', F.forward(xd)), ('bwd', F.backward(xd))):
+                rows = G.get(name, d + '_rows')
+                yh = host(y)
+                assert nerr(yh[rows], G.get(name, d), x, n) < tol, (d, lay, dt)
+                s = np.abs(yh.sum(axis=0) - G.get(name, d + '_sum')).max()
+                assert s / (np.linalg.norm(x, axis=0).max() * np.sqrt(n) * np.log2(n)) < tol * 10
+            assert torch.equal(xd, keep)              # the input is never modified (inspect/test.py:334-338)
+
+
+def test_fourier_dense_small(fm):
+    # the reference's own criterion: compare against the dense DFT matrix (no FFT involved), N in {35, 127}
+    for n in (35, 127, 64, 243):
+        F = fm.Fourier(n)
+        x = seeded(n, n, 5)
+        ref = host(F.reference()).dot(x)
+        assert nerr(host(F.forward(dev(x))), ref, x, n) < TOL128
+        assert nerr(host(F * dev(x)), ref, x, n) < TOL128             # operator interface
+
+
+def test_fourier_real_and_int_inputs(fm):
+    n = 256
+    F = fm.Fourier(n)
+    rng = np.random.default_rng(3)
+    for dt, out_dt, tol in ((np.float32, torch.complex64, TOL64), (np.float64, torch.complex128, TOL128),
+                            (np.int8, torch.complex64, TOL64), (np.int16, torch.complex64, TOL64),
+                            (np.int32, torch.complex128, TOL128), (np.int64, torch.complex128, TOL128)):
+        x = (rng.standard_normal((n, 3)) * 50).astype(dt)
+        y = F.forward(dev(x))
+        assert y.dtype == out_dt
+        assert nerr(host(y), np.fft.fft(x.astype(np.float64), axis=0), x, n) < tol
+
+
+def test_fourier_roundtrip_full_size(fm):
+    # property at the BASELINE size: backward(forward(x)) = N x; Parseval
+    n, m = 2 ** 20, 8
+    F = fm.Fourier(n)
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    x = torch.randn((m, n), dtype=torch.float32, device='cuda', generator=g).to(torch.complex64).t()
+    y = F.forward(x)
+    z = F.backward(y)
+    err = (z / n - x).abs().max().item() / x.abs().max().item()
+    assert err < 1e-4
+    e_in = torch.linalg.vector_norm(x, dim=0) ** 2
+    e_out = torch.linalg.vector_norm(y, dim=0) ** 2 / n
+    assert float(((e_in - e_out).abs() / e_in).max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- Circulant
+@pytest.mark.parametrize('name', G.cases('circulant'))
+def test_circulant_golden(fm, name):
+    p = G.params(name)
+    c, x = G.get(name, 'c'), G.get(name, 'x')
+    C = fm.Circulant(c, optimize=p.get('optimize', True))
+    check_pair(C, x, G.get(name, 'fwd'), x, G.get(name, 'bwd'), max(p['n'], 2))
+
+
+@pytest.mark.parametrize('name', G.cases('circulant_big'))
+def test_circulant_big_golden(fm, name):
+    p = G.params(name)
+    n = p['n']
+    c = seeded(p['seed_c'], n)
+    x = seeded(p['seed'], n, p['cols'])
+    for cdt, xdt, tol in ((np.complex128, np.complex128, TOL128), (np.complex64, np.complex64, TOL64)):
+        C = fm.Circulant(c.astype(cdt))
+        for lay in ('F', 'C'):
+            xd = dev(x.astype(xdt), lay)
+            for d, y in (('fwd', C.forward(xd)), ('bwd', C.backward(xd))):
+                assert y.dtype == (torch.complex128 if xdt == np.complex128 else torch.complex64)
+                rows = G.get(name, d + '_rows')
+                # ||C x|| scales with ||c||: normalise by ||c||_2 as well
+                e = nerr(host(y)[rows], G.get(name, d), x, n) / np.linalg.norm(c)
+                assert e < tol, (d, lay, e)
+
+
+@pytest.mark.parametrize('name', G.cases('circulant_ml'))
+def test_circulant_multilevel_golden(fm, name):
+    c, x = G.get(name, 'c'), G.get(name, 'x')
+    C = fm.Circulant(c)
+    n = x.shape[0]
+    assert nerr(host(C.forward(dev(x))), G.get(name, 'fwd'), x, n) / np.linalg.norm(c) < TOL128
+    assert nerr(host(C.backward(dev(x))), G.get(name, 'bwd'), x, n) / np.linalg.norm(c) < TOL128
+    ref = host(C.reference())
+    assert nerr(ref.dot(x), G.get(name, 'fwd'), x, n) / np.linalg.norm(c) < TOL128
+
+
+def test_circulant_properties_full_size(fm, orc):
+    # BASELINE config 2 shape (N = 2^20, complex64): adjoint identity, linearity, and two columns against the oracle
+    n, m = 2 ** 20, 16
+    rng = np.random.default_rng(4321)
+    c = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    C = fm.Circulant(c)
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    x = torch.complex(torch.randn((m, n), device='cuda', generator=g), torch.randn((m, n), device='cuda', generator=g)).t()
+    y = torch.complex(torch.randn((m, n), device='cuda', generator=g), torch.randn((m, n), device='cuda', generator=g)).t()
+    cx = C.forward(x)
+    chy = C.backward(y)
+    lhs = (cx.conj() * y).sum(dim=0)                  # <C x, y>
+    rhs = (x.conj() * chy).sum(dim=0)                 # <x, C^H y>
+    scale = torch.linalg.vector_norm(cx, dim=0) * torch.linalg.vector_norm(y, dim=0)
+    assert float(((lhs - rhs).abs() / scale).max()) < 1e-4
+    lin = C.forward(2 * x + y) - (2 * cx + C.forward(y))
+    assert float(lin.abs().max() / cx.abs().max()) < 1e-4
+    xh = host(x[:, :2])
+    ref = orc.circulant_forward(c, xh)
+    assert nerr(host(cx[:, :2]), ref, xh, n) / np.linalg.norm(c.astype(np.complex128)) < TOL64
+    refb = orc.circulant_backward(c, xh)
+    assert nerr(host(C.backward(x[:, :2])), refb, xh, n) / np.linalg.norm(c.astype(np.complex128)) < TOL64
+
+
+# ------------------------------------------------------------------------------------------- Toeplitz
+@pytest.mark.parametrize('name', G.cases('toeplitz'))
+def test_toeplitz_golden(fm, name):
+    p = G.params(name)
+    vc, vr, x, y = (G.get(name, k) for k in ('vc', 'vr', 'x', 'y'))
+    T = fm.Toeplitz(vc, vr)
+    assert T.shape == (p['n'], p['m'])
+    check_pair(T, x, G.get(name, 'fwd'), y, G.get(name, 'bwd'), max(p['n'] + p['m'], 2))
+    assert np.array_equal(host(T.reference()), __import__('oracle.fastmat_oracle', fromlist=['x']).dense_toeplitz(vc, vr))
+
+
+@pytest.mark.parametrize('name', G.cases('toeplitz_big'))
+def test_toeplitz_big_golden(fm, name):
+    p = G.params(name)
+    n, m = p['n'], p['m']
+    vc = seeded(p['seed_c'], n)
+    vr = seeded(p['seed_r'], m - 1)
+    x = seeded(p['seed_x'], m, p['cols'])
+    y = seeded(p['seed_y'], n, p['cols'])
+    nt = np.sqrt(np.linalg.norm(vc) ** 2 + np.linalg.norm(vr) ** 2)
+    for dt, tol in ((np.complex128, TOL128), (np.complex64, TOL64)):
+        T = fm.Toeplitz(vc.astype(dt), vr.astype(dt))
+        for lay in ('F', 'C'):
+            f = T.forward(dev(x.astype(dt), lay))
+            b = T.backward(dev(y.astype(dt), lay))
+            assert f.shape == (n, p['cols']) and b.shape == (m, p['cols'])
+            assert nerr(host(f)[G.get(name, 'fwd_rows')], G.get(name, 'fwd'), x, n + m) / nt < tol
+            assert nerr(host(b)[G.get(name, 'bwd_rows')], G.get(name, 'bwd'), y, n + m) / nt < tol
+
+
+@pytest.mark.parametrize('name', G.cases('toeplitz_ml'))
+def test_toeplitz_multilevel_golden(fm, name):
+    p = G.params(name)
+    t, x, y = G.get(name, 't'), G.get(name, 'x'), G.get(name, 'y')
+    T = fm.Toeplitz(t, split=p['split']) if p['split'] is not None else fm.Toeplitz(t)
+    n = t.size
+    assert nerr(host(T.forward(dev(x))), G.get(name, 'fwd'), x, n) / np.linalg.norm(t) < TOL128
+    assert nerr(host(T.backward(dev(y))), G.get(name, 'bwd'), y, n) / np.linalg.norm(t) < TOL128
+    assert nerr(host(T.reference()).dot(x), G.get(name, 'fwd'), x, n) / np.linalg.norm(t) < TOL128
+
+
+def test_toeplitz_full_size_adjoint(fm):
+    n = m = 2 ** 19
+    rng = np.random.default_rng(4321)
+    vc = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    vr = (rng.standard_normal(m - 1) + 1j * rng.standard_normal(m - 1)).astype(np.complex64)
+    T = fm.Toeplitz(vc, vr)
+    assert T._plan.info.inner_size == 2 ** 20
+    g = torch.Generator(device='cuda').manual_seed(99)
+    x = torch.complex(torch.randn((8, m), device='cuda', generator=g), torch.randn((8, m), device='cuda', generator=g)).t()
+    y = torch.complex(torch.randn((8, n), device='cuda', generator=g), torch.randn((8, n), device='cuda', generator=g)).t()
+    tx, thy = T.forward(x), T.backward(y)
+    lhs = (tx.conj() * y).sum(dim=0)
+    rhs = (x.conj() * thy).sum(dim=0)
+    scale = torch.linalg.vector_norm(tx, dim=0) * torch.linalg.vector_norm(y, dim=0)
+    assert float(((lhs - rhs).abs() / scale).max()) < 1e-4
+
+
+# ------------------------------------------------------------------------------------------- Hadamard
+@pytest.mark.parametrize('name', G.cases('hadamard'))
+def test_hadamard_golden_bit_exact(fm, name):
+    p = G.params(name)
+    x = G.get(name, 'x')
+    ref = G.get(name, 'fwd')
+    H = fm.Hadamard(p['order'])
+    for lay in ('F', 'C'):
+        xd = dev(x, lay)
+        keep = xd.clone()
+        y = host(H.forward(xd))
+        assert y.dtype == ref.dtype
+        assert np.array_equal(np.ascontiguousarray(y).view(np.uint8), np.ascontiguousarray(ref).view(np.uint8)), lay
+        yb = host(H.backward(xd))
+        assert np.array_equal(np.ascontiguousarray(yb).view(np.uint8), np.ascontiguousarray(ref).view(np.uint8))
+        assert torch.equal(xd, keep)
+
+
+@pytest.mark.parametrize('name', G.cases('hadamard_big'))
+def test_hadamard_big_golden_bit_exact(fm, name):
+    p = G.params(name)
+    x = seeded_typed(p['seed'], p['dtype'], 2 ** p['order'], p['cols'])
+    H = fm.Hadamard(p['order'])
+    ref = G.get(name, 'fwd')
+    for lay in ('F', 'C'):
+        y = host(H.forward(dev(x, lay)))
+        got = np.ascontiguousarray(y[G.get(name, 'fwd_rows')])
+        assert np.array_equal(got.view(np.uint8), np.ascontiguousarray(ref).view(np.uint8)), lay
+        if np.issubdtype(x.dtype, np.integer):
+            with np.errstate(over='ignore'):
+                assert np.array_equal(y.sum(axis=0, dtype=x.dtype), G.get(name, 'fwd_sum').astype(x.dtype))
+
+
+def test_hadamard_involution_full_size(fm):
+    # BASELINE config 3 shape: H(H(x)) = N x exactly for int32 (wrap-around arithmetic included)
+    order, m = 20, 8
+    H = fm.Hadamard(order)
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x = torch.randint(-2 ** 31, 2 ** 31 - 1, (m, 2 ** order), dtype=torch.int32, device='cuda', generator=g).t()
+    z = H.forward(H.forward(x))
+    assert torch.equal(z, x * (2 ** order))           # int32 arithmetic wraps identically on both sides
+    xf = torch.randn((m, 2 ** order), dtype=torch.float32, device='cuda', generator=g).t()
+    zf = H.forward(H.forward(xf))
+    assert float((zf / 2 ** order - xf).abs().max()) < 1e-3
+
+
+# ------------------------------------------------------------------------------------------- Kron
+@pytest.mark.parametrize('name', G.cases('kron_fourier'))
+def test_kron_fourier_golden(fm, name):
+    p = G.params(name)
+    x = G.get(name, 'x')
+    K = fm.Kron(*[fm.Fourier(d) for d in p['dims']])
+    assert (K._plan is not None) == (len(p['dims']) == 2)
+    check_pair(K, x, G.get(name, 'fwd'), x, G.get(name, 'bwd'), x.shape[0])
+
+
+def test_kron_fourier_big_golden(fm):
+    name = 'kronF_big_1024x1024'
+    p = G.params(name)
+    x = seeded(p['seed'], 2 ** 20, p['cols'])
+    K = fm.Kron(fm.Fourier(1024), fm.Fourier(1024))
+    for dt, tol in ((np.complex128, TOL128), (np.complex64, TOL64)):
+        for d, y in (('fwd', K.forward(dev(x.astype(dt)))), ('bwd', K.backward(dev(x.astype(dt))))):
+            assert nerr(host(y)[G.get(name, d + '_rows')], G.get(name, d), x, 2 ** 20) < tol
+
+
+def test_kron_mixed_and_dense_golden(fm):
+    name = 'kron_H3_F5'
+    x = G.get(name, 'x')
+    K = fm.Kron(fm.Hadamard(3), fm.Fourier(5))
+    assert nerr(host(K.forward(dev(x))), G.get(name, 'fwd'), x, 40) < TOL128
+    assert nerr(host(K.backward(dev(x))), G.get(name, 'bwd'), x, 40) < TOL128
+    name = 'kron_dense_5x4x3'
+    a = [G.get(name, 'a%d' % i) for i in range(3)]
+    x = G.get(name, 'x')
+    K = fm.Kron(*[fm.Matrix(m) for m in a])
+    assert nerr(host(K.forward(dev(x))), G.get(name, 'fwd'), x, 60) < 1e-12 * 60
+    assert nerr(host(K.backward(dev(x))), G.get(name, 'bwd'), x, 60) < 1e-12 * 60
+    with pytest.raises(ValueError):
+        fm.Kron(fm.Fourier(4))
+    with pytest.raises(ValueError):
+        fm.Kron(fm.Fourier(4), fm.Partial(fm.Fourier(4), rows=np.arange(2)))
+
+
+# ------------------------------------------------------------------------------------------- glue
+def test_partial_hadamard_golden_exact(fm):
+    name = 'partial_hadamard4'
+    rows, cols, x, y = (G.get(name, k) for k in ('rows', 'cols', 'x', 'y'))
+    P = fm.Partial(fm.Hadamard(4), rows=rows, cols=cols)
+    assert P.shape == (5, 4)
+    assert np.array_equal(host(P.forward(dev(x))), G.get(name, 'fwd'))
+    assert np.array_equal(host(P.backward(dev(y))), G.get(name, 'bwd'))
+    name = 'partial_hadamard4_bool'
+    P = fm.Partial(fm.Hadamard(4), rows=G.get(name, 'rows'))
+    assert np.array_equal(host(P.forward(dev(G.get(name, 'x')))), G.get(name, 'fwd'))
+    assert np.array_equal(host(P.backward(dev(G.get(name, 'y')))), G.get(name, 'bwd'))
+    with pytest.raises(ValueError):
+        fm.Partial(fm.Hadamard(4), rows=np.array([1, 16]))
+    with pytest.raises(TypeError):
+        fm.Partial(fm.Hadamard(4), rows=np.array([0.5, 1.0]))
+
+
+def test_cs_operator_golden(fm):
+    # BASELINE config 5's operator: Product(Partial(Fourier(n), rows=idx), Diag(d))
+    name = 'cs_partial_fourier_diag'
+    idx, d, x, y = (G.get(name, k) for k in ('idx', 'd', 'x', 'y'))
+    A = fm.Product(fm.Partial(fm.Fourier(256), rows=idx), fm.Diag(d))
+    assert A.shape == (64, 256)
+    assert nerr(host(A.forward(dev(x))), G.get(name, 'fwd'), x, 256) < TOL128
+    assert nerr(host(A.backward(dev(y))), G.get(name, 'bwd'), y, 256) < TOL128
+    A32 = fm.Product(fm.Partial(fm.Fourier(256), rows=idx), fm.Diag(d.astype(np.complex64)))
+    out = A32.forward(dev(x.astype(np.complex64)))
+    assert out.dtype == torch.complex64
+    assert nerr(host(out), G.get(name, 'fwd'), x, 256) < TOL64
+
+
+@pytest.mark.parametrize('name', G.cases('diag'))
+def test_diag_golden(fm, name):
+    d, x = G.get(name, 'd'), G.get(name, 'x')
+    D = fm.Diag(d)
+    for lay in ('F', 'C'):
+        f, b = host(D.forward(dev(x, lay))), host(D.backward(dev(x, lay)))
+        rf, rb = G.get(name, 'fwd'), G.get(name, 'bwd')
+        assert f.dtype == rf.dtype and b.dtype == rb.dtype
+        if np.issubdtype(rf.dtype, np.integer):
+            assert np.array_equal(f, rf) and np.array_equal(b, rb)
+        else:
+            tol = 1e-6 if rf.dtype in (np.float32, np.complex64) else 1e-14
+            assert np.abs(f - rf).max() <= tol * np.abs(rf).max()
+            assert np.abs(b - rb).max() <= tol * np.abs(rb).max()
+
+
+def test_permutation_golden_bit_exact(fm):
+    name = 'permutation_35'
+    sigma, x = G.get(name, 'sigma'), G.get(name, 'x')
+    P = fm.Permutation(sigma)
+    assert np.array_equal(host(P.forward(dev(x))), G.get(name, 'fwd'))
+    assert np.array_equal(host(P.backward(dev(x))), G.get(name, 'bwd'))
+    assert np.array_equal(host(P.forward(dev(x, 'C'))), G.get(name, 'fwd'))
+    with pytest.raises(ValueError):
+        fm.Permutation(np.array([0, 0, 1]))
+
+
+def test_sum_blocks_product_views_golden(fm):
+    name = 'sum_circ_diag_fourier'
+    c, d, x = G.get(name, 'c'), G.get(name, 'd'), G.get(name, 'x')
+    S = fm.Sum(fm.Circulant(c), fm.Diag(d), fm.Fourier(16))
+    assert nerr(host(S.forward(dev(x))), G.get(name, 'fwd'), x, 16) < 1e-12 * 10
+    assert nerr(host(S.backward(dev(x))), G.get(name, 'bwd'), x, 16) < 1e-12 * 10
+    S2 = fm.Circulant(c) + fm.Diag(d) + fm.Fourier(16)
+    assert nerr(host(S2.forward(dev(x))), G.get(name, 'fwd'), x, 16) < 1e-12 * 10
+    name = 'blocks_2x2'
+    c, d, x = G.get(name, 'c'), G.get(name, 'd'), G.get(name, 'x')
+    B = fm.Blocks([[fm.Circulant(c), fm.Fourier(16)], [fm.Diag(d), fm.Hadamard(4)]])
+    assert nerr(host(B.forward(dev(x))), G.get(name, 'fwd'), x, 32) < 1e-12 * 10
+    assert nerr(host(B.backward(dev(x))), G.get(name, 'bwd'), x, 32) < 1e-12 * 10
+    name = 'blockdiag'
+    x = G.get(name, 'x')
+    BD = fm.BlockDiag(fm.Fourier(16), fm.Hadamard(4))
+    assert nerr(host(BD.forward(dev(x))), G.get(name, 'fwd'), x, 32) < 1e-12 * 10
+    assert nerr(host(BD.backward(dev(x))), G.get(name, 'bwd'), x, 32) < 1e-12 * 10
+    name = 'product_scalar'
+    d, x = G.get(name, 'd'), G.get(name, 'x')
+    Pr = fm.Product(fm.Hadamard(4), 2.5 - 1j, fm.Diag(d), fm.Fourier(16))
+    assert nerr(host(Pr.forward(dev(x))), G.get(name, 'fwd'), x, 16) < 1e-12 * 100
+    assert nerr(host(Pr.backward(dev(x))), G.get(name, 'bwd'), x, 16) < 1e-12 * 100
+    Pr2 = fm.Hadamard(4) * (2.5 - 1j) * fm.Diag(d) * fm.Fourier(16)
+    assert nerr(host(Pr2.forward(dev(x))), G.get(name, 'fwd'), x, 16) < 1e-12 * 100
+    name = 'fourier_views'
+    x = G.get(name, 'x')
+    F = fm.Fourier(16)
+    assert nerr(host(F.H.forward(dev(x))), G.get(name, 'H'), x, 16) < TOL128
+    assert nerr(host(F.T.forward(dev(x))), G.get(name, 'T'), x, 16) < TOL128
+    assert nerr(host(F.conj.forward(dev(x))), G.get(name, 'conj'), x, 16) < TOL128
+    assert F.H.H is F and F.conj.conj is F
+
+
+# ------------------------------------------------------------------------------------------- interface behaviour
+def test_dimension_and_type_errors(fm):
+    F = fm.Fourier(16)
+    with pytest.raises(ValueError):
+        F.forward(torch.zeros(15, dtype=torch.complex64, device='cuda'))
+    with pytest.raises(ValueError):
+        F.forward(torch.zeros((16, 2, 2), dtype=torch.complex64, device='cuda'))
+    with pytest.raises(ValueError):
+        F.backward(torch.zeros((17, 2), dtype=torch.complex64, device='cuda'))
+    with pytest.raises(TypeError):
+        F.forward(torch.zeros(16, dtype=torch.float16, device='cuda'))
+    with pytest.raises(TypeError):
+        F.forward([0.0] * 16)
+    with pytest.raises(RuntimeError):
+        F.forward(torch.zeros(16, dtype=torch.complex64))                 # CPU tensor: no CPU path
+    for bad in (0, -3):
+        with pytest.raises(ValueError):
+            fm.Fourier(bad)
+    for bad in (0, 63):
+        with pytest.raises(ValueError):
+            fm.Hadamard(bad)
+    with pytest.raises(ValueError):
+        fm.Toeplitz(np.ones(3), np.ones(2), split=[2])
+    with pytest.raises(ValueError):
+        fm.Diag(np.ones((2, 2)))
+
+
+def test_strided_views_and_numpy_convenience(fm, orc):
+    n = 1024
+    rng = np.random.default_rng(11)
+    big = (rng.standard_normal((n, 12)) + 1j * rng.standard_normal((n, 12))).astype(np.complex64)
+    t = torch.from_numpy(big).cuda()
+    view = t[:, ::3]                                   # step-3 strided columns (inspect/common.py:478-521 "strided")
+    F = fm.Fourier(n)
+    ref = np.fft.fft(big[:, ::3].astype(np.complex128), axis=0)
+    assert nerr(host(F.forward(view)), ref, big[:, ::3], n) < TOL64
+    H = fm.Hadamard(10)
+    xi = rng.integers(-100, 100, size=(n, 12)).astype(np.int16)
+    vi = torch.from_numpy(xi).cuda()[:, 1::4]
+    assert np.array_equal(host(H.forward(vi)), orc.hadamard_forward(xi[:, 1::4]))
+    # numpy in -> numpy out (host round trip through the same C-ABI call)
+    y = F.forward(big[:, 0].copy())
+    assert isinstance(y, np.ndarray) and y.shape == (n, )
+    assert nerr(y, np.fft.fft(big[:, 0].astype(np.complex128)), big[:, 0], n) < TOL64
+
+
+def test_zero_columns_and_single_column(fm):
+    F = fm.Fourier(64)
+    y = F.forward(torch.zeros((64, 0), dtype=torch.complex64, device='cuda'))
+    assert y.shape == (64, 0)
+    x = torch.ones(64, dtype=torch.complex64, device='cuda')
+    y = F.forward(x)
+    assert y.shape == (64, ) and abs(y[0].item() - 64) < 1e-4 and float(y[1:].abs().max()) < 1e-4
+
+
+def test_launches_counted(fm):
+    before = fm.launch_count()
+    fm.Hadamard(8).forward(torch.ones((256, 4), dtype=torch.float32, device='cuda'))
+    assert fm.launch_count() > before
