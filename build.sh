@@ -5,7 +5,7 @@ set -euo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")"
 SRC=fastmat_b200/csrc
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-COMMON="-std=c++20 -O3 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas -Xcompiler -Wno-unused-but-set-variable -Xcompiler -Wno-unused-function -Iinclude --expt-relaxed-constexpr -diag-suppress 177,550"
+COMMON="-std=c++20 -O3 --extended-lambda -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas -Xcompiler -Wno-unused-but-set-variable -Xcompiler -Wno-unused-function -Iinclude --expt-relaxed-constexpr -diag-suppress 177,550"
 if [ "${EMUL:-0}" = "1" ]; then
   mkdir -p tests/emul
   $NVCC $COMMON -DFMB_EMULATE -gencode arch=compute_100a,code=sm_100a -shared -o tests/emul/libfmb_emul.so \
@@ -14,7 +14,7 @@ if [ "${EMUL:-0}" = "1" ]; then
 else
   mkdir -p fastmat_b200/lib build
   OBJS=""
-  for f in capi fft_engine fft_k_f32_pow2 fft_k_f32_gen fft_k_f64_pow2 fft_k_f64_gen fwht elementwise; do
+  for f in capi fft_engine fft_k_f32_pow2 fft_k_f32_gen fft_k_f64_pow2 fft_k_f64_gen fft_fast_f32_L8 fft_fast_f32_L9 fft_fast_f32_L10 fft_fast_f32_L11 fft_fast_f64_L8 fwht elementwise; do
     $NVCC $COMMON ${PTXAS_V:+-Xptxas -v} -gencode arch=compute_100a,code=sm_100a -c $SRC/$f.cu -o build/$f.o &
     OBJS="$OBJS build/$f.o"
   done

@@ -31,6 +31,8 @@ class Circulant(Matrix):
         tenC = _to_host(tenC)
         _t.getFusedType(tenC.dtype)
         self._tenC = np.array(np.squeeze(tenC), copy=True)
+        if self._tenC.ndim == 0 and tenC.ndim >= 1:
+            self._tenC = self._tenC.reshape(1)          # a 1 x 1 circulant stays one-dimensional
         if tenC.ndim < 1 or self._tenC.ndim < 1:
             raise ValueError("Column-definition tensor must be at least 1D.")
         self._default_device()

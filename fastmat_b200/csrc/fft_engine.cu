@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cmath>
 
+#include "fft_fast.cuh"
 #include "fft_pass.cuh"
 
 namespace fmb {
@@ -166,6 +167,13 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
         unit_roots(L, (L + B - 1) / B, B, w);
         rc = upload_cvec<C>(d.twH, w);
         if (rc) return rc;
+        // fast path: twS[g][i] = W_L^{(R_g / 16) i}, i < L / R_g (step of the four-step twiddle along a thread's outputs)
+        for (int g = 0; g < 2; ++g) {
+            const int64_t Rg = shape.g[g].R;
+            if (Rg % 16) continue;
+            unit_roots(L, L / Rg, Rg / 16, w);
+            if ((rc = upload_cvec<C>(d.twS[g], w))) return rc;
+        }
     }
     int rc;
     if (!pre.empty() && (rc = upload_cvec<C>(d.pre, pre))) return rc;
@@ -175,11 +183,18 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
     return FMB_OK;
 }
 
+static long env_long(const char *name, long dflt) {
+    const char *v = getenv(name);
+    return v ? atol(v) : dflt;
+}
+
 int ConvEngine::slab_cols(int64_t M, size_t csize) const {
     if (shape.npass == 1) return (int)std::min<int64_t>(M, 1 << 30);
     // keep the intermediate of a slab inside L2 (about a third of it: the streamed input/output passes through too)
     size_t l2 = device_props().l2_bytes ? device_props().l2_bytes : (size_t)100 << 20;
     size_t budget = l2 / 3;
+    static const long slab_mb = env_long("FMB_SLAB_MB", 0);          // tuning knob (experiments only)
+    if (slab_mb > 0) budget = (size_t)slab_mb << 20;
     int64_t s = (int64_t)(budget / ((size_t)L * csize));
     if (s < 1) s = 1;
     return (int)std::min<int64_t>(s, M);
@@ -197,8 +212,9 @@ static TileChoice choose_tile(const PassGeom &g, size_t csize, bool pow2, bool a
     TileChoice tc;
     const int R = g.R;
     int64_t maxT = std::max<int64_t>(1, pass_limit(g) / R);
-    int64_t T = std::max<int64_t>(1, 4096 / R);
-    if (wide_t) T = std::max<int64_t>(T, 8);
+    static const long tile_elems = env_long("FMB_TILE_ELEMS", 4096), wide_min = env_long("FMB_WIDE_T", 8);
+    int64_t T = std::max<int64_t>(1, tile_elems / R);
+    if (wide_t) T = std::max<int64_t>(T, wide_min);
     T = std::min(T, maxT);
     // do not make tiles much wider than the work available
     int64_t lp = pow2 ? next_pow2(lines) : lines;
@@ -257,6 +273,121 @@ template <typename C> static PassParams<C> blank_params() {
     return p;
 }
 
+// ------------------------------------------------------------------------------------------- fast path (fft_fast.cuh)
+// pass variants (must match fft_fast_inst.cuh)
+static const unsigned FV_A_F_ = FO_LOAD_T | FO_TWIDDLE, FV_A_FC_ = FV_A_F_ | FO_IN_CONJ, FV_A_M_ = FV_A_F_ | FO_IN_MASK,
+                      FV_A_MP_ = FV_A_M_ | FO_PRE, FV_A_MPC_ = FV_A_MP_ | FO_PRE_CONJ,
+                      FV_B_F_ = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK, FV_B_FC_ = FV_B_F_ | FO_OUT_CONJ,
+                      FV_BM_ = FO_LOAD_T | FO_STORE_T | FO_TWO_FFTS | FO_TWIDDLE, FV_BMC_ = FV_BM_ | FO_MID_CONJ,
+                      FV_C_M_ = FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK, FV_C_MP_ = FV_C_M_ | FO_POST,
+                      FV_C_MPC_ = FV_C_MP_ | FO_POST_CONJ;
+int launch_fast_f32_L8(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f32_L9(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f32_L10(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f32_L11(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f64_L8(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
+
+static bool fast_has(const float2 *, int logr) { return logr >= 8 && logr <= 11; }
+static bool fast_has(const double2 *, int logr) { return logr == 8; }
+static int fast_logt(const float2 *, int logr) { return FastTile<8>::LOGT * 0 + ((logr <= 9) ? (12 - logr) : (13 - logr)); }
+static int fast_logt(const double2 *, int logr) { return ((logr <= 9) ? (12 - logr) : (13 - logr)) - 1; }
+static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
+    switch (logr) {
+        case 8: return launch_fast_f32_L8(opt, a, tiles, st);
+        case 9: return launch_fast_f32_L9(opt, a, tiles, st);
+        case 10: return launch_fast_f32_L10(opt, a, tiles, st);
+        default: return launch_fast_f32_L11(opt, a, tiles, st);
+    }
+}
+static int fast_launch(int, unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st) {
+    return launch_fast_f64_L8(opt, a, tiles, st);
+}
+static int ilog2_host(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return l; }
+
+template <typename C> bool ConvEngine::fast_ok(int64_t xrs, int64_t yrs, bool in_real) const {
+#ifdef FMB_EMULATE
+    return false;
+#else
+    static const long off = env_long("FMB_NO_FAST", 0);
+    if (off || !shape.pow2 || shape.npass != 2 || kron_a > 0 || in_real || xrs != 1 || yrs != 1) return false;
+    if (L >= ((int64_t)1 << 30)) return false;
+    return fast_has((const C *)nullptr, ilog2_host(shape.g[0].R)) && fast_has((const C *)nullptr, ilog2_host(shape.g[1].R));
+#endif
+}
+
+// column-major power-of-two transforms: the same three (two) passes as below with compile-time geometry
+template <typename C>
+int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const {
+#ifdef FMB_EMULATE
+    return FMB_ERR_NOTIMPL;
+#else
+    const bool bwd = direction == FMB_BACKWARD;
+    const int64_t rows_in = bwd ? n_out : n_in, rows_out = bwd ? n_in : n_out;
+    const C *pre_d = (const C *)(bwd ? d.post.p : d.pre.p);
+    const C *post_d = (const C *)(bwd ? d.pre.p : d.post.p);
+    const int R1 = shape.g[0].R, R2 = shape.g[1].R;
+    const int l1 = ilog2_host(R1), l2 = ilog2_host(R2);
+    const int t1 = fast_logt((const C *)nullptr, l1), t2 = fast_logt((const C *)nullptr, l2);
+    const int64_t slab = slab_cols(M, sizeof(C));
+    int rc;
+    for (int64_t c0 = 0; c0 < M; c0 += slab) {
+        const int64_t nc = std::min(slab, M - c0);
+        FastArgs<C> base;
+        memset(&base, 0, sizeof(base));
+        base.ncols = (int)nc;
+        base.twL = (const C *)d.twL.p; base.twH = (const C *)d.twH.p; base.tw_shift = d.tw_shift;
+        base.tw_mask = (unsigned)(((int64_t)1 << d.tw_shift) - 1);
+        // ---- pass A: length R1 over n = f*R2 + i, lines i < R2; out: ws[c][i][k] (k contiguous)
+        {
+            FastArgs<C> a = base;
+            a.in = (const C *)x + c0 * xcs; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
+            a.out = (C *)ws; a.out_cs = L; a.out_ks = 1; a.out_is = R1;
+            a.I = R2; a.logI = l2;
+            a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
+            a.wR = (const C *)d.wR[0].p; a.twS = (const C *)d.twS[0].p;
+            a.pre = pre_d;
+            unsigned opt;
+            if (!two_ffts) opt = bwd ? FV_A_FC_ : FV_A_F_;
+            else if (pre_d) opt = bwd ? FV_A_MPC_ : FV_A_MP_;
+            else opt = (rows_in < L) ? FV_A_M_ : FV_A_F_;
+            if ((rc = fast_launch(l1, opt, a, (unsigned)((nc * R2) >> t1), st))) return rc;
+        }
+        if (!two_ffts) {
+            // ---- pass B: length R2 over f = n2 (stride R1 in ws), lines i = k1 < R1; out y[k*R1 + i]
+            FastArgs<C> a = base;
+            a.in = (const C *)ws; a.in_cs = L; a.in_fs = R1; a.in_is = 1;
+            a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
+            a.I = R1; a.logI = l1;
+            a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
+            a.wR = (const C *)d.wR[1].p;
+            if ((rc = fast_launch(l2, bwd ? FV_B_FC_ : FV_B_F_, a, (unsigned)((nc * R1) >> t2), st))) return rc;
+        } else {
+            {   // ---- pass B': in place on ws; FFT over n2, * spectrum[k*R1 + i], conj, FFT, * W^{ik}
+                FastArgs<C> a = base;
+                a.in = (const C *)ws; a.in_cs = L; a.in_fs = R1; a.in_is = 1;
+                a.out = (C *)ws; a.out_cs = L; a.out_ks = R1; a.out_is = 1;
+                a.I = R1; a.logI = l1;
+                a.mid = (const C *)d.mid.p; a.mid_ks = R1;
+                a.wR = (const C *)d.wR[1].p; a.twS = (const C *)d.twS[1].p;
+                if ((rc = fast_launch(l2, bwd ? FV_BMC_ : FV_BM_, a, (unsigned)((nc * R1) >> t2), st))) return rc;
+            }
+            {   // ---- pass C: length R1 over f = k1 (contiguous in ws rows), lines i = m2 < R2; out y[k*R2 + i]
+                FastArgs<C> a = base;
+                a.in = (const C *)ws; a.in_cs = L; a.in_fs = 1; a.in_is = R1;
+                a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R2; a.out_is = 1;
+                a.I = R2; a.logI = l2;
+                a.out_n = (int)rows_out; a.out_lk = R2; a.out_li = 1;
+                a.post = post_d;
+                a.wR = (const C *)d.wR[0].p;
+                unsigned opt = post_d ? (bwd ? FV_C_MPC_ : FV_C_MP_) : FV_C_M_;
+                if ((rc = fast_launch(l1, opt, a, (unsigned)((nc * R2) >> t1), st))) return rc;
+            }
+        }
+    }
+    return FMB_OK;
+#endif
+}
+
 template <typename C>
 int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t xcs, bool in_real, void *y, int64_t yrs,
                       int64_t ycs, int64_t M, void *ws, int64_t ws_bytes, cudaStream_t st) const {
@@ -292,6 +423,7 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
         set_error("workspace too small: need %lld bytes", (long long)(slab * L * (int64_t)sizeof(C)));
         return FMB_ERR_WORKSPACE;
     }
+    if (fast_ok<C>(xrs, yrs, in_real)) return run_fast<C>(d, direction, x, xcs, y, ycs, M, ws, st);
     const int64_t R1 = shape.g[0].R, R2 = shape.g[1].R;
     const bool kron = kron_a > 0;
     for (int64_t c0 = 0; c0 < M; c0 += slab) {

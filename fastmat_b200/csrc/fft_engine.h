@@ -40,7 +40,7 @@ struct ConvEngine {
     FftShape shape;
 
     struct Dev {
-        DevArray wR[2], twL, twH, pre, post, mid;
+        DevArray wR[2], twL, twH, twS[2], pre, post, mid;
         int tw_shift = 0;
         bool ready = false;
     };
@@ -59,6 +59,9 @@ struct ConvEngine {
 
    private:
     template <typename C> int ensure_dev(Dev &d) const;
+    template <typename C> bool fast_ok(int64_t xrs, int64_t yrs, bool in_real) const;
+    template <typename C>
+    int run_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const;
     template <typename C>
     int run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t xcs, bool in_real, void *y, int64_t yrs, int64_t ycs,
               int64_t M, void *ws, int64_t ws_bytes, cudaStream_t st) const;

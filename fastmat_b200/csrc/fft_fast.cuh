@@ -1,0 +1,282 @@
+// Fast path of the FFT / convolution engine: power-of-two transforms in fastmat's column-major layout.
+//
+// Same algorithm as fft_pass.cuh (four-step FFT over an L2-resident intermediate; Stockham radix-16 stages staged in
+// shared memory) but with the pass length R, the tile width T, the radix plan and every fused option fixed at compile
+// time, so that all shared-memory offsets are immediates, there is no per-element flag test, and a thread's sixteen
+// values stay in registers from the global load to the first exchange and from the last exchange to the global store.
+//
+// Thread t of a CTA owns, in every stage, the sixteen transform positions  jb + (R/16) m, m = 0..15  of one line
+// (jb = its "row", the line = its "column"): a radix-P stage treats them as 16/P butterflies.  Two thread orders
+// exist: line-fastest (consecutive threads walk the T lines of the tile: used whenever the lines are the contiguous
+// direction in global memory) and row-fastest (consecutive threads walk jb: used when the transform axis is
+// contiguous).  Shared memory is laid out [line][position] with one pad element per 16 positions and a line stride
+// of 4 (mod 16) elements, which makes both orders bank-conflict free (see DESIGN.md "shared-memory layout").
+#pragma once
+#include "cx.cuh"
+
+namespace fmb {
+
+template <int LOGR> struct FastPlan;      // radix plan: first stage radix 16 (Ns = 1), then 16s, then the remainder
+template <> struct FastPlan<7>  { static constexpr int S = 2; static constexpr int P0 = 16, P1 = 8,  P2 = 1; };
+template <> struct FastPlan<8>  { static constexpr int S = 2; static constexpr int P0 = 16, P1 = 16, P2 = 1; };
+template <> struct FastPlan<9>  { static constexpr int S = 3; static constexpr int P0 = 16, P1 = 16, P2 = 2; };
+template <> struct FastPlan<10> { static constexpr int S = 3; static constexpr int P0 = 16, P1 = 16, P2 = 4; };
+template <> struct FastPlan<11> { static constexpr int S = 3; static constexpr int P0 = 16, P1 = 16, P2 = 8; };
+template <> struct FastPlan<12> { static constexpr int S = 3; static constexpr int P0 = 16, P1 = 16, P2 = 16; };
+
+template <int LOGR> struct FastTile {     // lines per tile (log2): 4096 or 8192 elements per CTA
+    static constexpr int LOGT = (LOGR <= 9) ? (12 - LOGR) : (13 - LOGR);
+};
+
+template <int LOGR, int LOGT> struct FastGeom {
+    static constexpr int R = 1 << LOGR, T = 1 << LOGT, ROWS = R / 16, NT = ROWS * T;
+    // line stride in shared memory: R positions + one pad per 16, then padded so that RS == 32/T (mod 16): with that
+    // residue the 32 lanes of a warp (T lines x 32/T rows in line-fastest order) hit every bank pair exactly twice
+    static constexpr int WANT = (32 >> LOGT) & 15;
+    static constexpr int RS = R + R / 16 + ((WANT - (R + R / 16)) % 16 + 16) % 16;
+    static constexpr int SMEM_ELEMS = T * RS;
+};
+
+// runtime arguments of one fast pass (everything structural is a template parameter)
+template <typename C> struct FastArgs {
+    typedef typename real_of<C>::type S;
+    const C *in;                 // element (f, line) at in[col*in_cs + f*in_fs + i*in_is]
+    C *out;                      // element (k, line) at out[col*out_cs + k*out_ks + i*out_is]
+    long long in_cs, out_cs;     // column strides (elements)
+    int in_fs, in_is, out_ks, out_is;
+    int I;                       // lines per column (power of two), log2 in logI
+    int logI;
+    int ncols;
+    int in_n, in_lf, in_li;      // load mask: logical row f*in_lf + i*in_li must be < in_n
+    int out_n, out_lk, out_li;   // store mask
+    const C *wR;                 // exp(-2 pi i j / R)
+    const C *twL, *twH;          // four-step twiddle W_N^e = twL[e & mask] * twH[e >> shift]
+    int tw_shift; unsigned tw_mask;
+    const C *twS;                // twS[i] = W_N^{(R/16) i}
+    const C *mid;                // spectrum: element (k, i) at mid[k*mid_ks + i]
+    int mid_ks;
+    const C *pre, *post;         // indexed by logical row
+};
+
+// option bits of a pass
+enum : unsigned {
+    FO_LOAD_T = 1u,        // first stage line-fastest (else row-fastest)
+    FO_STORE_T = 2u,       // last stage line-fastest
+    FO_TWIDDLE = 4u,       // multiply the output by W_N^{i k}
+    FO_TWO_FFTS = 8u,      // FFT -> * mid -> conj -> FFT
+    FO_MID_CONJ = 16u,     // use conj(mid)
+    FO_IN_CONJ = 32u,
+    FO_OUT_CONJ = 64u,
+    FO_IN_MASK = 128u,
+    FO_OUT_MASK = 256u,
+    FO_PRE = 512u, FO_PRE_CONJ = 1024u,
+    FO_POST = 2048u, FO_POST_CONJ = 4096u,
+    FO_IN_CG = 8192u,      // the input was written by other SMs in this launch (read through L2 only)
+};
+
+template <typename C> __device__ __forceinline__ C ld_cg(const C *p) { return __ldcg(p); }
+
+// one radix-P stage on the sixteen register values of a thread.
+//   v[m] holds position jb + ROWS*m on entry (natural Stockham input order of every stage) and, on exit, the values
+//   are written through `store(k, value)` at their Stockham output positions.
+template <typename C, int LOGR, int P, int NS, typename Store>
+__device__ __forceinline__ void fast_butterflies(C (&v)[16], int jb, const C *__restrict__ wR, Store store) {
+    constexpr int R = 1 << LOGR, ROWS = R / 16, NBF = 16 / P, TWS = R / (NS * P);
+#pragma unroll
+    for (int it = 0; it < NBF; ++it) {
+        const int j = jb + it * ROWS;
+        C u[P];
+#pragma unroll
+        for (int r = 0; r < P; ++r) u[r] = v[it + NBF * r];
+        if (NS > 1) {
+            const int kk = j & (NS - 1);
+#pragma unroll
+            for (int r = 1; r < P; ++r) u[r] = cmul(u[r], __ldg(wR + kk * r * TWS));
+        }
+        if constexpr (P == 2) dft2(u[0], u[1]);
+        else if constexpr (P == 4) dft4(u[0], u[1], u[2], u[3]);
+        else if constexpr (P == 8) dft8(u);
+        else dft16(u);
+        const int j0 = (NS * P == R) ? j : (((j & ~(NS - 1)) * P) | (j & (NS - 1)));   // last stage: j < NS
+#pragma unroll
+        for (int q = 0; q < P; ++q) store(j0 + q * NS, u[outpos<P>(q)], it, q);
+    }
+}
+
+template <int P_, int NS_> struct FastTag { static constexpr int P = P_, NS = NS_; };
+
+template <int LOGR, int LOGT, bool ORDER_T> __device__ __forceinline__ void fast_thread_pos(int tid, int &jb, int &t) {
+    constexpr int ROWS = (1 << LOGR) / 16, T = 1 << LOGT;
+    if (ORDER_T) { t = tid & (T - 1); jb = tid >> LOGT; }
+    else { jb = tid & (ROWS - 1); t = tid >> (LOGR - 4); }
+}
+
+// The whole pass for one tile.  `tile` indexes T consecutive lines; line = col*I + i.
+template <typename C, int LOGR, int LOGT, unsigned OPT>
+__device__ __forceinline__ void fast_pass_tile(const FastArgs<C> &a, unsigned tile, C *smem) {
+    typedef FastGeom<LOGR, LOGT> G;
+    typedef FastPlan<LOGR> PL;
+    constexpr int R = G::R, ROWS = G::ROWS, RS = G::RS;
+    constexpr bool LOAD_T = (OPT & FO_LOAD_T) != 0, STORE_T = (OPT & FO_STORE_T) != 0, TWO = (OPT & FO_TWO_FFTS) != 0;
+    constexpr int NS1 = PL::P0, NS2 = PL::P0 * PL::P1;
+    const int tid = threadIdx.x;
+    const unsigned line0 = tile << LOGT;
+    const unsigned col = line0 >> a.logI;                  // T divides I: a tile never straddles two columns
+    const unsigned i0 = line0 & (unsigned)(a.I - 1);
+    C v[16];
+    int jb, t;
+
+    // ------------------------------------------------------------------ stage 0: global -> registers -> shared
+    fast_thread_pos<LOGR, LOGT, LOAD_T>(tid, jb, t);
+    {
+        const unsigned i = i0 + t;
+        const C *src = a.in + (long long)col * a.in_cs + (long long)i * a.in_is + (long long)jb * a.in_fs;
+#pragma unroll
+        for (int m = 0; m < 16; ++m) {
+            const int f = jb + ROWS * m;
+            bool ok = true;
+            if (OPT & FO_IN_MASK) ok = (f * a.in_lf + (int)i * a.in_li) < a.in_n;
+            C val = mk<C>(0, 0);
+            if (ok) {
+                const C *p = src + (long long)(ROWS * m) * a.in_fs;
+                val = (OPT & FO_IN_CG) ? ld_cg(p) : *p;
+                if (OPT & FO_IN_CONJ) val = cconj(val);
+                if (OPT & FO_PRE) {
+                    const C w = __ldg(a.pre + (f * a.in_lf + (int)i * a.in_li));
+                    val = (OPT & FO_PRE_CONJ) ? cmulc(val, w) : cmul(val, w);
+                }
+            }
+            v[m] = val;
+        }
+    }
+    C *sline = smem + t * RS;
+    fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, a.wR, [&](int k, C val, int, int) { sline[k + (k >> 4)] = val; });
+    __syncthreads();
+
+    constexpr bool INNER_T = LOAD_T;                       // inner stages keep the load order (any order is conflict free)
+    // ------------------------------------------------------------------ stage 1 (and 2): shared -> shared, or the last stage
+    auto load16 = [&](const C *sl, int jb_) {
+        const C *b = sl + jb_ + (jb_ >> 4);
+#pragma unroll
+        for (int m = 0; m < 16; ++m) v[m] = b[ROWS * m + (ROWS * m >> 4)];      // ROWS*m is a multiple of 16 when ROWS >= 16
+    };
+    static_assert(ROWS % 16 == 0 || ROWS == 8, "row count must keep the pad offsets separable");
+    auto load16g = [&](const C *sl, int jb_) {
+        if constexpr (ROWS % 16 == 0) load16(sl, jb_);
+        else {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) { const int f = jb_ + ROWS * m; v[m] = sl[f + (f >> 4)]; }
+        }
+    };
+
+    // generic "last stage + global store" used by both the single and the second transform
+    auto final_store = [&](int jb_, int t_, auto stage_tag) {
+        constexpr int P = decltype(stage_tag)::P, NS = decltype(stage_tag)::NS;
+        const unsigned i = i0 + t_;
+        C *dst = a.out + (long long)col * a.out_cs + (long long)i * a.out_is;
+        // four-step twiddle of output k = jb + ROWS*(it + NBF*q):  W^{i jb} * (W^{ROWS i})^{it} * ((W^{ROWS i})^{NBF})^q
+        constexpr int NBF = 16 / P;
+        C wbase = mk<C>(1, 0), s1 = mk<C>(1, 0), sq = mk<C>(1, 0), wcur = mk<C>(1, 0);
+        if (OPT & FO_TWIDDLE) {
+            const unsigned e = i * (unsigned)jb_;
+            wbase = cmul(__ldg(a.twL + (e & a.tw_mask)), __ldg(a.twH + (e >> a.tw_shift)));
+            s1 = __ldg(a.twS + i);
+            sq = s1;                                  // sq = s1^NBF by repeated squaring (NBF is a power of two)
+#pragma unroll
+            for (int b2 = 1; b2 < NBF; b2 *= 2) sq = cmul(sq, sq);
+        }
+        fast_butterflies<C, LOGR, P, NS>(v, jb_, a.wR, [&](int k, C val, int it, int q) {
+            if (OPT & FO_TWIDDLE) {
+                if (q == 0) {                          // start of butterfly `it`: wcur = wbase * s1^it
+                    if (it > 0) wbase = cmul(wbase, s1);
+                    wcur = wbase;
+                } else {
+                    wcur = cmul(wcur, sq);
+                }
+                val = cmul(val, wcur);
+            }
+            if (OPT & FO_OUT_CONJ) val = cconj(val);
+            bool ok = true;
+            const int mrow = k * a.out_lk + (int)i * a.out_li;
+            if (OPT & FO_OUT_MASK) ok = mrow < a.out_n;
+            if (OPT & FO_POST) {
+                if (ok) {
+                    const C pw = __ldg(a.post + mrow);
+                    val = (OPT & FO_POST_CONJ) ? cmulc(val, pw) : cmul(val, pw);
+                }
+            }
+            if (ok) dst[(long long)k * a.out_ks] = val;
+        });
+    };
+
+    typedef FastTag<PL::P1, NS1> Tag1;
+    typedef FastTag<PL::P2, NS2> Tag2;
+
+    auto smem_store = [&](C *sl) { return [sl](int k, C val, int, int) { sl[k + (k >> 4)] = val; }; };
+
+    if constexpr (!TWO) {
+        if constexpr (PL::S == 2) {
+            fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
+            load16g(smem + t * RS, jb);
+            final_store(jb, t, Tag1());
+        } else {
+            fast_thread_pos<LOGR, LOGT, INNER_T>(tid, jb, t);
+            load16g(smem + t * RS, jb);
+            __syncthreads();
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
+            __syncthreads();
+            fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
+            load16g(smem + t * RS, jb);
+            final_store(jb, t, Tag2());
+        }
+    } else {
+        // ---- finish the first transform in shared memory
+        fast_thread_pos<LOGR, LOGT, INNER_T>(tid, jb, t);
+        load16g(smem + t * RS, jb);
+        __syncthreads();
+        fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
+        __syncthreads();
+        if constexpr (PL::S == 3) {
+            load16g(smem + t * RS, jb);
+            __syncthreads();
+            fast_butterflies<C, LOGR, PL::P2, NS2>(v, jb, a.wR, smem_store(smem + t * RS));
+            __syncthreads();
+        }
+        // ---- spectrum multiply + conj fused into the first load of the second transform
+        load16g(smem + t * RS, jb);
+        {
+            const unsigned i = i0 + t;
+            const C *mp = a.mid + i + (long long)jb * a.mid_ks;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const C w = __ldg(mp + (long long)(ROWS * m) * a.mid_ks);
+                v[m] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[m], w) : cmul(v[m], w));
+            }
+        }
+        __syncthreads();
+        fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, a.wR, smem_store(smem + t * RS));
+        __syncthreads();
+        if constexpr (PL::S == 2) {
+            fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
+            load16g(smem + t * RS, jb);
+            final_store(jb, t, Tag1());
+        } else {
+            load16g(smem + t * RS, jb);
+            __syncthreads();
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
+            __syncthreads();
+            fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
+            load16g(smem + t * RS, jb);
+            final_store(jb, t, Tag2());
+        }
+    }
+}
+
+template <typename C, int LOGR, int LOGT, unsigned OPT>
+__global__ void __launch_bounds__(FastGeom<LOGR, LOGT>::NT, (FastGeom<LOGR, LOGT>::NT >= 512 ? 2 : 3))
+fast_pass_kernel(const __grid_constant__ FastArgs<C> a) {
+    extern __shared__ __align__(16) unsigned char fmb_fast_smem[];
+    fast_pass_tile<C, LOGR, LOGT, OPT>(a, blockIdx.x, reinterpret_cast<C *>(fmb_fast_smem));
+}
+
+}  // namespace fmb

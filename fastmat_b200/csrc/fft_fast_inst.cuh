@@ -1,0 +1,55 @@
+// One translation unit per (precision, log2 R) instantiates the twelve pass variants of the fast path.
+#pragma once
+#include "common.h"
+#include "fft_fast.cuh"
+
+namespace fmb {
+
+// the pass variants the engine uses (see fft_engine.cu: run_fast)
+constexpr unsigned FV_A_F = FO_LOAD_T | FO_TWIDDLE;                                   // first pass, plain
+constexpr unsigned FV_A_FC = FV_A_F | FO_IN_CONJ;                                     // first pass of conj(F conj x)
+constexpr unsigned FV_A_M = FV_A_F | FO_IN_MASK;                                      // first pass, zero-padded input
+constexpr unsigned FV_A_MP = FV_A_M | FO_PRE;                                         // ... with pre-multiply (chirp)
+constexpr unsigned FV_A_MPC = FV_A_MP | FO_PRE_CONJ;
+constexpr unsigned FV_B_F = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK;                     // second pass of a plain transform
+constexpr unsigned FV_B_FC = FV_B_F | FO_OUT_CONJ;
+constexpr unsigned FV_BM = FO_LOAD_T | FO_STORE_T | FO_TWO_FFTS | FO_TWIDDLE;         // middle pass of a convolution
+constexpr unsigned FV_BMC = FV_BM | FO_MID_CONJ;
+constexpr unsigned FV_C_M = FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK;                   // last pass of a convolution
+constexpr unsigned FV_C_MP = FV_C_M | FO_POST;
+constexpr unsigned FV_C_MPC = FV_C_MP | FO_POST_CONJ;
+
+template <typename C, int LOGR, unsigned OPT>
+int launch_fast_variant(const FastArgs<C> &a, unsigned tiles, cudaStream_t st) {
+    constexpr int LOGT = FastTile<LOGR>::LOGT + (sizeof(C) == 16 ? -1 : 0);            // complex128: half the lines per tile
+    typedef FastGeom<LOGR, LOGT> G;
+    const size_t smem = (size_t)G::SMEM_ELEMS * sizeof(C);
+    static int attr_done = 0;
+    if (!attr_done) {
+        FMB_CUDA_OK(cudaFuncSetAttribute(fast_pass_kernel<C, LOGR, LOGT, OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = 1;
+    }
+    fast_pass_kernel<C, LOGR, LOGT, OPT><<<tiles, G::NT, smem, st>>>(a);
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+}
+
+template <typename C, int LOGR> int launch_fast_logr(unsigned opt, const FastArgs<C> &a, unsigned tiles, cudaStream_t st) {
+    switch (opt) {
+        case FV_A_F: return launch_fast_variant<C, LOGR, FV_A_F>(a, tiles, st);
+        case FV_A_FC: return launch_fast_variant<C, LOGR, FV_A_FC>(a, tiles, st);
+        case FV_A_M: return launch_fast_variant<C, LOGR, FV_A_M>(a, tiles, st);
+        case FV_A_MP: return launch_fast_variant<C, LOGR, FV_A_MP>(a, tiles, st);
+        case FV_A_MPC: return launch_fast_variant<C, LOGR, FV_A_MPC>(a, tiles, st);
+        case FV_B_F: return launch_fast_variant<C, LOGR, FV_B_F>(a, tiles, st);
+        case FV_B_FC: return launch_fast_variant<C, LOGR, FV_B_FC>(a, tiles, st);
+        case FV_BM: return launch_fast_variant<C, LOGR, FV_BM>(a, tiles, st);
+        case FV_BMC: return launch_fast_variant<C, LOGR, FV_BMC>(a, tiles, st);
+        case FV_C_M: return launch_fast_variant<C, LOGR, FV_C_M>(a, tiles, st);
+        case FV_C_MP: return launch_fast_variant<C, LOGR, FV_C_MP>(a, tiles, st);
+        case FV_C_MPC: return launch_fast_variant<C, LOGR, FV_C_MPC>(a, tiles, st);
+        default: set_error("fast path: unknown pass variant %u", opt); return FMB_ERR_NOTIMPL;
+    }
+}
+
+}  // namespace fmb

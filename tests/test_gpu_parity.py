@@ -88,6 +88,12 @@ def test_fourier_big_golden(fm, name):
     x = seeded(p['seed'], n, p['cols'])
     F = fm.Fourier(n, optimize=p['optimize'])
     assert F._numL == p['numL']                       # the reference's Bluestein decision is reproduced
+    # When the reference takes its chirp-z branch it forms k^2 * pi / N in float64 (fastmat/Fourier.pyx:130), which
+    # costs it ~1e-10 at N = 1e6; the device path reduces k^2 mod 2N in integers first and is MORE accurate.  Those
+    # cases are therefore compared with the reference at 1e-9 and, at full tolerance, with pocketfft's direct DFT.
+    direct = None
+    if p['numL'] > 0:
+        direct = {'fwd': np.fft.fft(x, axis=0), 'bwd': np.conj(np.fft.fft(np.conj(x), axis=0))}
     for lay in ('F', 'C'):
         for dt, tol in ((np.complex128, TOL128), (np.complex64, TOL64)):
             xd = dev(x.astype(dt), lay)
@@ -95,7 +101,11 @@ def test_fourier_big_golden(fm, name):
             for d, y in (('fwd', F.forward(xd)), ('bwd', F.backward(xd))):
                 rows = G.get(name, d + '_rows')
                 yh = host(y)
-                assert nerr(yh[rows], G.get(name, d), x, n) < tol, (d, lay, dt)
+                if direct is not None:
+                    assert nerr(yh, direct[d], x, n) < tol, (d, lay, dt, 'vs direct DFT')
+                    assert nerr(yh[rows], G.get(name, d), x, n) < max(tol, 1e-9), (d, lay, dt)
+                else:
+                    assert nerr(yh[rows], G.get(name, d), x, n) < tol, (d, lay, dt)
                 s = np.abs(yh.sum(axis=0) - G.get(name, d + '_sum')).max()
                 assert s / (np.linalg.norm(x, axis=0).max() * np.sqrt(n) * np.log2(n)) < tol * 10
             assert torch.equal(xd, keep)              # the input is never modified (inspect/test.py:334-338)
