@@ -5,7 +5,7 @@ set -euo pipefail
 cd "$(dirname "${BASH_SOURCE[0]}")"
 SRC=fastmat_b200/csrc
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
-COMMON="-std=c++20 -O3 --extended-lambda -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas -Xcompiler -Wno-unused-but-set-variable -Xcompiler -Wno-unused-function -Iinclude --expt-relaxed-constexpr -diag-suppress 177,550"
+COMMON="${EXTRA_DEFS:-} -std=c++20 -O3 --extended-lambda -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas -Xcompiler -Wno-unused-but-set-variable -Xcompiler -Wno-unused-function -Iinclude --expt-relaxed-constexpr -diag-suppress 177,550"
 if [ "${EMUL:-0}" = "1" ]; then
   mkdir -p tests/emul
   $NVCC $COMMON -DFMB_EMULATE -gencode arch=compute_100a,code=sm_100a -shared -o tests/emul/libfmb_emul.so \

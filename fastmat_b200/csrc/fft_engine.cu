@@ -289,8 +289,8 @@ int launch_fast_f64_L8(unsigned opt, const FastArgs<double2> &a, unsigned tiles,
 
 static bool fast_has(const float2 *, int logr) { return logr >= 8 && logr <= 11; }
 static bool fast_has(const double2 *, int logr) { return logr == 8; }
-static int fast_logt(const float2 *, int logr) { return FastTile<8>::LOGT * 0 + ((logr <= 9) ? (12 - logr) : (13 - logr)); }
-static int fast_logt(const double2 *, int logr) { return ((logr <= 9) ? (12 - logr) : (13 - logr)) - 1; }
+static int fast_logt(const float2 *, int logr) { return (logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr); }
+static int fast_logt(const double2 *, int logr) { return ((logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr)) - 1; }
 static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
     switch (logr) {
         case 8: return launch_fast_f32_L8(opt, a, tiles, st);

@@ -25,14 +25,18 @@ template <> struct FastPlan<11> { static constexpr int S = 3; static constexpr i
 template <> struct FastPlan<12> { static constexpr int S = 3; static constexpr int P0 = 16, P1 = 16, P2 = 16; };
 
 template <int LOGR> struct FastTile {     // lines per tile (log2): 4096 or 8192 elements per CTA
-    static constexpr int LOGT = (LOGR <= 9) ? (12 - LOGR) : (13 - LOGR);
+#ifndef FMB_FAST_TILE_LOG2
+#define FMB_FAST_TILE_LOG2 13
+#endif
+    static constexpr int LOGT = (LOGR <= 9) ? (12 - LOGR) : (FMB_FAST_TILE_LOG2 - LOGR);
 };
 
 template <int LOGR, int LOGT> struct FastGeom {
     static constexpr int R = 1 << LOGR, T = 1 << LOGT, ROWS = R / 16, NT = ROWS * T;
-    // line stride in shared memory: R positions + one pad per 16, then padded so that RS == 32/T (mod 16): with that
-    // residue the 32 lanes of a warp (T lines x 32/T rows in line-fastest order) hit every bank pair exactly twice
-    static constexpr int WANT = (32 >> LOGT) & 15;
+    // line stride in shared memory: R positions + one pad per 16, then padded so that RS == 16/T (mod 16): a 64-bit
+    // access is served per half-warp, and with that residue the 16 lanes of a half-warp (T lines x 16/T rows in
+    // line-fastest order) fall on 16 different bank pairs
+    static constexpr int WANT = (16 >> LOGT) ? (16 >> LOGT) : 1;
     static constexpr int RS = R + R / 16 + ((WANT - (R + R / 16)) % 16 + 16) % 16;
     static constexpr int SMEM_ELEMS = T * RS;
 };
@@ -76,6 +80,19 @@ enum : unsigned {
 
 template <typename C> __device__ __forceinline__ C ld_cg(const C *p) { return __ldcg(p); }
 
+// read-only load that the compiler may not hoist across other memory operations: keeps the sixteen spectrum loads of the
+// middle pass from all being issued (and held in registers) before the butterfly that consumes them
+__device__ __forceinline__ float2 ld_nc_pinned(const float2 *p) {
+    float2 r;
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    return r;
+}
+__device__ __forceinline__ double2 ld_nc_pinned(const double2 *p) {
+    double2 r;
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    return r;
+}
+
 // one radix-P stage on the sixteen register values of a thread.
 //   v[m] holds position jb + ROWS*m on entry (natural Stockham input order of every stage) and, on exit, the values
 //   are written through `store(k, value)` at their Stockham output positions.
@@ -112,8 +129,10 @@ template <int LOGR, int LOGT, bool ORDER_T> __device__ __forceinline__ void fast
 }
 
 // The whole pass for one tile.  `tile` indexes T consecutive lines; line = col*I + i.
-template <typename C, int LOGR, int LOGT, unsigned OPT>
-__device__ __forceinline__ void fast_pass_tile(const FastArgs<C> &a, unsigned tile, C *smem) {
+// PART: 0 = the whole pass; for two-transform passes 1 = up to the spectrum multiply, 2 = the second transform.  The two
+// halves are compiled as separate (non-inlined) functions so that each gets its own 64-register allocation.
+template <typename C, int LOGR, int LOGT, unsigned OPT, int PART>
+__device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned tile, C *smem) {
     typedef FastGeom<LOGR, LOGT> G;
     typedef FastPlan<LOGR> PL;
     constexpr int R = G::R, ROWS = G::ROWS, RS = G::RS;
@@ -128,7 +147,7 @@ __device__ __forceinline__ void fast_pass_tile(const FastArgs<C> &a, unsigned ti
 
     // ------------------------------------------------------------------ stage 0: global -> registers -> shared
     fast_thread_pos<LOGR, LOGT, LOAD_T>(tid, jb, t);
-    {
+    if constexpr (PART != 2) {
         const unsigned i = i0 + t;
         const C *src = a.in + (long long)col * a.in_cs + (long long)i * a.in_is + (long long)jb * a.in_fs;
 #pragma unroll
@@ -148,10 +167,10 @@ __device__ __forceinline__ void fast_pass_tile(const FastArgs<C> &a, unsigned ti
             }
             v[m] = val;
         }
+        C *sline = smem + t * RS;
+        fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, a.wR, [&](int k, C val, int, int) { sline[k + (k >> 4)] = val; });
+        __syncthreads();
     }
-    C *sline = smem + t * RS;
-    fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, a.wR, [&](int k, C val, int, int) { sline[k + (k >> 4)] = val; });
-    __syncthreads();
 
     constexpr bool INNER_T = LOAD_T;                       // inner stages keep the load order (any order is conflict free)
     // ------------------------------------------------------------------ stage 1 (and 2): shared -> shared, or the last stage
@@ -230,29 +249,34 @@ __device__ __forceinline__ void fast_pass_tile(const FastArgs<C> &a, unsigned ti
             final_store(jb, t, Tag2());
         }
     } else {
-        // ---- finish the first transform in shared memory
+        // ---- finish the first transform in shared memory; its last stage multiplies every output X[k] by the spectrum
+        //      (and conjugates: the second transform runs the inverse as conj(FFT(conj(.))))
         fast_thread_pos<LOGR, LOGT, INNER_T>(tid, jb, t);
+        if constexpr (PART != 2) {
+        const C *mp = a.mid + (i0 + t);
+        auto mid_store = [&](C *sl) {
+            return [sl, mp, &a](int k, C val, int, int) {
+                const C w = __ldg(mp + (long long)k * a.mid_ks);
+                sl[k + (k >> 4)] = cconj((OPT & FO_MID_CONJ) ? cmulc(val, w) : cmul(val, w));
+            };
+        };
         load16g(smem + t * RS, jb);
         __syncthreads();
-        fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
-        __syncthreads();
-        if constexpr (PL::S == 3) {
+        if constexpr (PL::S == 2) {
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, mid_store(smem + t * RS));
+            __syncthreads();
+        } else {
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
+            __syncthreads();
             load16g(smem + t * RS, jb);
             __syncthreads();
-            fast_butterflies<C, LOGR, PL::P2, NS2>(v, jb, a.wR, smem_store(smem + t * RS));
+            fast_butterflies<C, LOGR, PL::P2, NS2>(v, jb, a.wR, mid_store(smem + t * RS));
             __syncthreads();
         }
-        // ---- spectrum multiply + conj fused into the first load of the second transform
-        load16g(smem + t * RS, jb);
-        {
-            const unsigned i = i0 + t;
-            const C *mp = a.mid + i + (long long)jb * a.mid_ks;
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const C w = __ldg(mp + (long long)(ROWS * m) * a.mid_ks);
-                v[m] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[m], w) : cmul(v[m], w));
-            }
         }
+        if constexpr (PART != 1) {
+        // ---- second transform
+        load16g(smem + t * RS, jb);
         __syncthreads();
         fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, a.wR, smem_store(smem + t * RS));
         __syncthreads();
@@ -269,6 +293,23 @@ __device__ __forceinline__ void fast_pass_tile(const FastArgs<C> &a, unsigned ti
             load16g(smem + t * RS, jb);
             final_store(jb, t, Tag2());
         }
+        }
+    }
+}
+
+template <typename C, int LOGR, int LOGT, unsigned OPT, int PART>
+__device__ __noinline__ void fast_pass_half(const FastArgs<C> &a, unsigned tile) {
+    extern __shared__ __align__(16) unsigned char fmb_fast_smem[];
+    fast_pass_part<C, LOGR, LOGT, OPT, PART>(a, tile, reinterpret_cast<C *>(fmb_fast_smem));
+}
+
+template <typename C, int LOGR, int LOGT, unsigned OPT>
+__device__ __forceinline__ void fast_pass_tile(const FastArgs<C> &a, unsigned tile, C *smem) {
+    if constexpr (OPT & FO_TWO_FFTS) {
+        fast_pass_half<C, LOGR, LOGT, OPT, 1>(a, tile);
+        fast_pass_half<C, LOGR, LOGT, OPT, 2>(a, tile);
+    } else {
+        fast_pass_part<C, LOGR, LOGT, OPT, 0>(a, tile, smem);
     }
 }
 

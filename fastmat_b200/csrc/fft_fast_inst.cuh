@@ -21,7 +21,7 @@ constexpr unsigned FV_C_MPC = FV_C_MP | FO_POST_CONJ;
 
 template <typename C, int LOGR, unsigned OPT>
 int launch_fast_variant(const FastArgs<C> &a, unsigned tiles, cudaStream_t st) {
-    constexpr int LOGT = FastTile<LOGR>::LOGT + (sizeof(C) == 16 ? -1 : 0);            // complex128: half the lines per tile
+    constexpr int LOGT = FastTile<LOGR>::LOGT - (sizeof(C) == 16 ? 1 : 0);              // complex128: half the lines per tile
     typedef FastGeom<LOGR, LOGT> G;
     const size_t smem = (size_t)G::SMEM_ELEMS * sizeof(C);
     static int attr_done = 0;
