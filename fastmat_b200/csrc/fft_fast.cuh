@@ -132,7 +132,8 @@ template <int LOGR, int LOGT, bool ORDER_T> __device__ __forceinline__ void fast
 // PART: 0 = the whole pass; for two-transform passes 1 = up to the spectrum multiply, 2 = the second transform.  The two
 // halves are compiled as separate (non-inlined) functions so that each gets its own 64-register allocation.
 template <typename C, int LOGR, int LOGT, unsigned OPT, int PART>
-__device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned tile, C *smem) {
+__device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned tile, C *smem, long long in_off = 0,
+                                               long long out_off = 0) {
     typedef FastGeom<LOGR, LOGT> G;
     typedef FastPlan<LOGR> PL;
     constexpr int R = G::R, ROWS = G::ROWS, RS = G::RS;
@@ -149,7 +150,7 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
     fast_thread_pos<LOGR, LOGT, LOAD_T>(tid, jb, t);
     if constexpr (PART != 2) {
         const unsigned i = i0 + t;
-        const C *src = a.in + (long long)col * a.in_cs + (long long)i * a.in_is + (long long)jb * a.in_fs;
+        const C *src = a.in + in_off + (long long)col * a.in_cs + (long long)i * a.in_is + (long long)jb * a.in_fs;
 #pragma unroll
         for (int m = 0; m < 16; ++m) {
             const int f = jb + ROWS * m;
@@ -192,7 +193,7 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
     auto final_store = [&](int jb_, int t_, auto stage_tag) {
         constexpr int P = decltype(stage_tag)::P, NS = decltype(stage_tag)::NS;
         const unsigned i = i0 + t_;
-        C *dst = a.out + (long long)col * a.out_cs + (long long)i * a.out_is;
+        C *dst = a.out + out_off + (long long)col * a.out_cs + (long long)i * a.out_is;
         // four-step twiddle of output k = jb + ROWS*(it + NBF*q):  W^{i jb} * (W^{ROWS i})^{it} * ((W^{ROWS i})^{NBF})^q
         constexpr int NBF = 16 / P;
         C wbase = mk<C>(1, 0), s1 = mk<C>(1, 0), sq = mk<C>(1, 0), wcur = mk<C>(1, 0);
@@ -298,9 +299,20 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
 }
 
 template <typename C, int LOGR, int LOGT, unsigned OPT, int PART>
-__device__ __noinline__ void fast_pass_half(const FastArgs<C> &a, unsigned tile) {
+__device__ __noinline__ void fast_pass_half(const FastArgs<C> &a, unsigned tile, long long in_off = 0, long long out_off = 0) {
     extern __shared__ __align__(16) unsigned char fmb_fast_smem[];
-    fast_pass_part<C, LOGR, LOGT, OPT, PART>(a, tile, reinterpret_cast<C *>(fmb_fast_smem));
+    fast_pass_part<C, LOGR, LOGT, OPT, PART>(a, tile, reinterpret_cast<C *>(fmb_fast_smem), in_off, out_off);
+}
+
+// a whole pass as non-inlined function(s): used by the fused persistent kernel, where several pass types share one kernel
+template <typename C, int LOGR, int LOGT, unsigned OPT>
+__device__ __forceinline__ void fast_pass_call(const FastArgs<C> &a, unsigned tile, long long in_off, long long out_off) {
+    if constexpr (OPT & FO_TWO_FFTS) {
+        fast_pass_half<C, LOGR, LOGT, OPT, 1>(a, tile, in_off, out_off);
+        fast_pass_half<C, LOGR, LOGT, OPT, 2>(a, tile, in_off, out_off);
+    } else {
+        fast_pass_half<C, LOGR, LOGT, OPT, 0>(a, tile, in_off, out_off);
+    }
 }
 
 template <typename C, int LOGR, int LOGT, unsigned OPT>

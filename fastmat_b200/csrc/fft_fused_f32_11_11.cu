@@ -1,0 +1,4 @@
+#include "fft_fused_inst.cuh"
+namespace fmb {
+int launch_fused_f32_11_11(int variant, const FusedArgs<float2> &g, cudaStream_t st) { return launch_fused_pair<float2, 11, 11>(variant, g, st); }
+}  // namespace fmb
