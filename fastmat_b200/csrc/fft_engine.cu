@@ -191,10 +191,11 @@ static long env_long(const char *name, long dflt) {
 
 int ConvEngine::slab_cols(int64_t M, size_t csize) const {
     if (shape.npass == 1) return (int)std::min<int64_t>(M, 1 << 30);
-    // keep the intermediate of a slab inside L2 (about a third of it: the streamed input/output passes through too)
-    size_t l2 = device_props().l2_bytes ? device_props().l2_bytes : (size_t)100 << 20;
-    size_t budget = l2 / 3;
-    static const long slab_mb = env_long("FMB_SLAB_MB", 0);          // tuning knob (experiments only)
+    // Columns pushed through all passes together.  Measured on B200 (round 1): launches over few columns (an
+    // L2-sized slab) lose more to launch gaps and partial waves than they gain from the L2-resident intermediate, so
+    // the slab is sized by a workspace budget (512 MiB) instead; FMB_SLAB_MB overrides it for experiments.
+    size_t budget = (size_t)512 << 20;
+    static const long slab_mb = env_long("FMB_SLAB_MB", 0);
     if (slab_mb > 0) budget = (size_t)slab_mb << 20;
     int64_t s = (int64_t)(budget / ((size_t)L * csize));
     if (s < 1) s = 1;
@@ -444,8 +445,11 @@ template <typename C> bool ConvEngine::fused_ok() const {
 #ifdef FMB_EMULATE
     return false;
 #else
-    static const long off = env_long("FMB_NO_FUSED", 0);
-    if (off) return false;
+    // The fused persistent pipeline (fft_fused.cuh) keeps HBM traffic at the algorithmic minimum but, as measured on
+    // B200 in round 1, its per-tile scheduling overhead makes it slower than one launch per pass (DESIGN.md "status of
+    // the fused kernel"); it is therefore opt-in until that overhead is gone.
+    static const long on = env_long("FMB_FUSED", 0);
+    if (!on) return false;
     return fused_has((const C *)nullptr, ilog2_host(shape.g[0].R), ilog2_host(shape.g[1].R));
 #endif
 }
