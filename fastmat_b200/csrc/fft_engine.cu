@@ -284,7 +284,8 @@ static const unsigned FV_A_F_ = FO_LOAD_T | FO_TWIDDLE, FV_A_FC_ = FV_A_F_ | FO_
                       FV_B_F_ = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK, FV_B_FC_ = FV_B_F_ | FO_OUT_CONJ,
                       FV_BM_ = FO_LOAD_T | FO_STORE_T | FO_TWO_FFTS | FO_TWIDDLE, FV_BMC_ = FV_BM_ | FO_MID_CONJ,
                       FV_C_M_ = FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK, FV_C_MP_ = FV_C_M_ | FO_POST,
-                      FV_C_MPC_ = FV_C_MP_ | FO_POST_CONJ;
+                      FV_C_MPC_ = FV_C_MP_ | FO_POST_CONJ, FV_K_AC_ = FV_B_F_ | FO_IN_CONJ, FV_K_B_ = FO_OUT_MASK,
+                      FV_K_BC_ = FO_OUT_MASK | FO_OUT_CONJ;
 int launch_fast_f32_L8(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L9(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L10(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
@@ -313,7 +314,7 @@ template <typename C> bool ConvEngine::fast_ok(int64_t xrs, int64_t yrs, bool in
     return false;
 #else
     static const long off = env_long("FMB_NO_FAST", 0);
-    if (off || !shape.pow2 || shape.npass != 2 || kron_a > 0 || in_real || xrs != 1 || yrs != 1) return false;
+    if (off || !shape.pow2 || shape.npass != 2 || in_real || xrs != 1 || yrs != 1) return false;
     if (L >= ((int64_t)1 << 30)) return false;
     return fast_has((const C *)nullptr, ilog2_host(shape.g[0].R)) && fast_has((const C *)nullptr, ilog2_host(shape.g[1].R));
 #endif
@@ -341,6 +342,24 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
         base.ncols = (int)nc;
         base.twL = (const C *)d.twL.p; base.twH = (const C *)d.twH.p; base.tw_shift = d.tw_shift;
         base.tw_mask = (unsigned)(((int64_t)1 << d.tw_shift) - 1);
+        if (kron_a > 0) {
+            // Kron(Fourier(R1), Fourier(R2)): 2-D transform of the row-major (R1, R2) image, no twiddle between the passes
+            FastArgs<C> a = base;                                     // over i1 (stride R2), lines i2; natural order out
+            a.in = (const C *)x + c0 * xcs; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
+            a.out = (C *)ws; a.out_cs = L; a.out_ks = R2; a.out_is = 1;
+            a.I = R2; a.logI = l2;
+            a.out_n = (int)L; a.out_lk = R2; a.out_li = 1;
+            a.wR = (const C *)d.wR[0].p;
+            if ((rc = fast_launch(l1, bwd ? FV_K_AC_ : FV_B_F_, a, (unsigned)((nc * R2) >> t1), st))) return rc;
+            FastArgs<C> b2 = base;                                    // over i2 (contiguous), lines k1
+            b2.in = (const C *)ws; b2.in_cs = L; b2.in_fs = 1; b2.in_is = R2;
+            b2.out = (C *)y + c0 * ycs; b2.out_cs = ycs; b2.out_ks = 1; b2.out_is = R2;
+            b2.I = R1; b2.logI = l1;
+            b2.out_n = (int)L; b2.out_lk = 1; b2.out_li = R2;
+            b2.wR = (const C *)d.wR[1].p;
+            if ((rc = fast_launch(l2, bwd ? FV_K_BC_ : FV_K_B_, b2, (unsigned)((nc * R1) >> t2), st))) return rc;
+            continue;
+        }
         // ---- pass A: length R1 over n = f*R2 + i, lines i < R2; out: ws[c][i][k] (k contiguous)
         {
             FastArgs<C> a = base;
@@ -449,7 +468,7 @@ template <typename C> bool ConvEngine::fused_ok() const {
     // B200 in round 1, its per-tile scheduling overhead makes it slower than one launch per pass (DESIGN.md "status of
     // the fused kernel"); it is therefore opt-in until that overhead is gone.
     static const long on = env_long("FMB_FUSED", 0);
-    if (!on) return false;
+    if (!on || kron_a > 0) return false;
     return fused_has((const C *)nullptr, ilog2_host(shape.g[0].R), ilog2_host(shape.g[1].R));
 #endif
 }

@@ -18,6 +18,9 @@ constexpr unsigned FV_BMC = FV_BM | FO_MID_CONJ;
 constexpr unsigned FV_C_M = FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK;                   // last pass of a convolution
 constexpr unsigned FV_C_MP = FV_C_M | FO_POST;
 constexpr unsigned FV_C_MPC = FV_C_MP | FO_POST_CONJ;
+constexpr unsigned FV_K_AC = FV_B_F | FO_IN_CONJ;                                    // Kron: first pass of the backward
+constexpr unsigned FV_K_B = FO_OUT_MASK;                                             // Kron: second pass (rows contiguous)
+constexpr unsigned FV_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
 
 template <typename C, int LOGR, unsigned OPT>
 int launch_fast_variant(const FastArgs<C> &a, unsigned tiles, cudaStream_t st) {
@@ -48,6 +51,9 @@ template <typename C, int LOGR> int launch_fast_logr(unsigned opt, const FastArg
         case FV_C_M: return launch_fast_variant<C, LOGR, FV_C_M>(a, tiles, st);
         case FV_C_MP: return launch_fast_variant<C, LOGR, FV_C_MP>(a, tiles, st);
         case FV_C_MPC: return launch_fast_variant<C, LOGR, FV_C_MPC>(a, tiles, st);
+        case FV_K_AC: return launch_fast_variant<C, LOGR, FV_K_AC>(a, tiles, st);
+        case FV_K_B: return launch_fast_variant<C, LOGR, FV_K_B>(a, tiles, st);
+        case FV_K_BC: return launch_fast_variant<C, LOGR, FV_K_BC>(a, tiles, st);
         default: set_error("fast path: unknown pass variant %u", opt); return FMB_ERR_NOTIMPL;
     }
 }

@@ -199,9 +199,174 @@ template <typename T> static int launch_fwht_pass(const FwhtPass &p, cudaStream_
 #endif
 }
 
+// ------------------------------------------------------------------------------------------- fast path
+// Column-major arrays, order >= 8: every thread keeps sixteen values in registers per sub-stage (four index bits, taken
+// in ascending order so the result stays bit-identical to the reference), sub-stages exchange through padded shared
+// memory, the first sub-stage reads global memory directly and the last one writes it directly.
+struct FwhtFastPass {
+    const void *in;
+    void *out;
+    long long in_cs, out_cs;   // column strides (elements); row stride is 1
+    int b, s;                  // this pass transforms index bits [s, s+b)
+    int logT;                  // lines (consecutive low-bit values) per tile; 0 for the contiguous first pass
+    int order;
+    long long tiles_per_col;
+};
+
+template <typename T> __device__ __forceinline__ void fwht16(T (&v)[16], int lev0) {
+#pragma unroll
+    for (int lev = 0; lev < 4; ++lev) {
+        if (lev < lev0) continue;                       // bits below lev0 were transformed by the previous sub-stage
+        const int d = 1 << lev;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if ((r & d) == 0) {
+                const T a = v[r], b = v[r | d];
+                v[r] = HOps<T>::add(a, b);
+                v[r | d] = HOps<T>::sub(a, b);
+            }
+        }
+    }
+}
+
+template <typename T> __global__ void __launch_bounds__(512) fwht_fast_kernel(const __grid_constant__ FwhtFastPass p) {
+    extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
+    T *sm = reinterpret_cast<T *>(fwht_smem_raw);
+    const int tid = threadIdx.x;
+    const int b = p.b, logT = p.logT, Tn = 1 << logT;
+    const int nq = 1 << (b - 4);                        // threads per line
+    const long long col = blockIdx.x / p.tiles_per_col;
+    const long long tin = blockIdx.x - col * p.tiles_per_col;
+    // tile -> (hi, lo0): the tile covers all 2^b mid values, Tn consecutive lo values starting at lo0, one hi value
+    const long long lo_tiles = ((long long)1 << p.s) >> logT;
+    const long long hi = tin / lo_tiles, lo0 = (tin - hi * lo_tiles) << logT;
+    const long long base = (hi << (p.s + b)) + lo0;
+    const T *gin = (const T *)p.in + col * p.in_cs + base;
+    T *gout = (T *)p.out + col * p.out_cs + base;
+    const int t = tid & (Tn - 1), q = tid >> logT;      // line-fastest thread order
+    const int RSL = (1 << b) + ((1 << b) >> 4) + 1;     // padded line stride in shared memory
+    T *sl = sm + t * RSL;
+    T v[16];
+    int u = 0;
+    // ---- first sub-stage: bits [0, 4) of mid straight from global memory
+    {
+        const long long step = (long long)1 << p.s;
+        const T *src = gin + (long long)(q << 4) * step + t;
+        if (p.s == 0 && sizeof(T) == 4 && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {   // contiguous: 4 x 128-bit loads
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                float4 f = s4[r];
+                v[4 * r + 0] = reinterpret_cast<T &>(f.x); v[4 * r + 1] = reinterpret_cast<T &>(f.y);
+                v[4 * r + 2] = reinterpret_cast<T &>(f.z); v[4 * r + 3] = reinterpret_cast<T &>(f.w);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = src[(long long)r * step];
+        }
+        fwht16<T>(v, 0);
+        u = 4;
+        if (b == 4) {                                   // a single sub-stage: back to global memory directly
+            T *dst = gout + (long long)(q << 4) * step + t;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dst[(long long)r * step] = v[r];
+            return;
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { const int m = (q << 4) + r; sl[m + (m >> 4)] = v[r]; }
+    }
+    __syncthreads();
+    // ---- middle sub-stages in shared memory, last sub-stage to global memory
+    for (;;) {
+        int lev0 = 0;
+        int uu = u;
+        if (u + 4 > b) { uu = b - 4; lev0 = u - uu; }    // fewer than four bits left: re-use the top four, skip done levels
+        const int l = q & ((1 << uu) - 1), h = q >> uu;
+        const int m0 = (h << (uu + 4)) | l;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { const int m = m0 + (r << uu); v[r] = sl[m + (m >> 4)]; }
+        fwht16<T>(v, lev0);
+        if (uu + 4 >= b) {                              // last sub-stage
+            const long long step = (long long)1 << p.s;
+            T *dst = gout + (long long)m0 * step + t;
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dst[(long long)(r << uu) * step] = v[r];
+            return;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { const int m = m0 + (r << uu); sl[m + (m >> 4)] = v[r]; }
+        __syncthreads();
+        u += 4;
+        (void)nq;
+    }
+}
+
+template <typename T>
+static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, cudaStream_t st) {
+    // bit ranges per pass: a contiguous first pass of up to 12 bits, then strided passes of 4..8 bits
+    std::vector<int> bits;
+    if (order <= 12) bits.push_back(order);
+    else {
+        int rem = order - 12;
+        if (rem < 4) { bits.push_back(order - 4); bits.push_back(4); }
+        else {
+            bits.push_back(12);
+            int np = (rem + 7) / 8, basev = rem / np, extra = rem % np;
+            for (int i = 0; i < np; ++i) bits.push_back(basev + (i < extra ? 1 : 0));
+        }
+    }
+    const int tile_elems = (int)std::min<size_t>(8192, std::max<size_t>(512, (size_t)32768 / sizeof(T)));   // <= 512 threads x 16
+    static int attr_done = 0;
+    if (!attr_done) {
+        FMB_CUDA_OK(cudaFuncSetAttribute(fwht_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
+        attr_done = 1;
+    }
+    size_t l2 = device_props().l2_bytes ? device_props().l2_bytes : (size_t)100 << 20;
+    static const long slab_mb = getenv("FMB_FWHT_SLAB_MB") ? atol(getenv("FMB_FWHT_SLAB_MB")) : 0;
+    size_t budget = slab_mb > 0 ? (size_t)slab_mb << 20 : l2 / 3;
+    int64_t slab = (int64_t)(budget / (((size_t)1 << order) * sizeof(T)));
+    if (slab < 1) slab = 1;
+    if (bits.size() == 1) slab = M;
+    for (int64_t c0 = 0; c0 < M; c0 += slab) {
+        const int64_t nc = std::min<int64_t>(slab, M - c0);
+        int s = 0;
+        for (size_t pi = 0; pi < bits.size(); ++pi) {
+            FwhtFastPass p;
+            memset(&p, 0, sizeof(p));
+            const bool first = (pi == 0);
+            p.in = first ? (const char *)x + (size_t)(c0 * xcs) * sizeof(T) : (const char *)y + (size_t)(c0 * ycs) * sizeof(T);
+            p.in_cs = first ? xcs : ycs;
+            p.out = (char *)y + (size_t)(c0 * ycs) * sizeof(T);
+            p.out_cs = ycs;
+            p.b = bits[pi]; p.s = s; p.order = order;
+            int logT = 0;
+            if (s > 0) {
+                int want = tile_elems >> p.b;                      // lines per tile
+                while ((1 << (logT + 1)) <= want && (logT + 1) <= s) ++logT;
+            }
+            p.logT = logT;
+            const int threads = (1 << (p.b - 4)) << logT;
+            p.tiles_per_col = ((long long)1 << (order - p.b)) >> logT;
+            const long long grid = p.tiles_per_col * nc;
+            if (grid > 2147483647LL || threads > 512 || threads < 1) { set_error("FWHT fast path: bad geometry"); return FMB_ERR_VALUE; }
+            const size_t smem = (size_t)(1 << logT) * ((size_t)(1 << p.b) + ((size_t)(1 << p.b) >> 4) + 1) * sizeof(T);
+            fwht_fast_kernel<T><<<(unsigned)grid, threads, smem, st>>>(p);
+            FMB_LAUNCH_OK();
+            s += p.b;
+        }
+    }
+    return FMB_OK;
+}
+
 template <typename T>
 static int fwht_typed(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, cudaStream_t st) {
     const bool row_major = (xcs == 1 && M > 1);
+#ifndef FMB_EMULATE
+    static const long no_fast = getenv("FMB_NO_FAST") ? atol(getenv("FMB_NO_FAST")) : 0;
+    if (!no_fast && !row_major && xrs == 1 && yrs == 1 && order >= 8 && order <= 40)
+        return fwht_fast<T>(order, x, xcs, y, ycs, M, st);
+#endif
     // ---- split the bits into passes
     const int tile_bytes = 64 << 10;
     std::vector<int> bits;

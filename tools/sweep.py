@@ -16,6 +16,16 @@ def timed(f, k=5):
     for _ in range(k): f()
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / k
+if len(sys.argv) > 2 and sys.argv[2] == 'hadamard':
+    H = fm.Hadamard(20)
+    xf = torch.randn((cols * 2, N), device='cuda').t()
+    th = timed(lambda: H.forward(xf))
+    gbh = 8.0 * N * cols * 2 / 1e9
+    print("env FWHT_SLAB_MB=%s | hadamard o20 f32 %d cols: %.2f ms %.0f GB/s (%.1f%%)" % (os.environ.get('FMB_FWHT_SLAB_MB'), cols * 2, th, gbh / th * 1e3, gbh / th * 1e3 / 65.539))
+    xi = torch.randint(-2**31, 2**31 - 1, (64, N), device='cuda', dtype=torch.int32).t()
+    z = H.forward(H.forward(xi))
+    print("involution int32 exact:", bool(torch.equal(z, xi * N)))
+    sys.exit(0)
 C = fm.Circulant(c); F = fm.Fourier(N)
 tc = timed(lambda: C.forward(x)); tf = timed(lambda: F.forward(x))
 gb = 16.0 * N * cols / 1e9
