@@ -213,10 +213,9 @@ struct FwhtFastPass {
     long long tiles_per_col;
 };
 
-template <typename T> __device__ __forceinline__ void fwht16(T (&v)[16], int lev0) {
+template <typename T, int LEV0> __device__ __forceinline__ void fwht16(T (&v)[16]) {
 #pragma unroll
-    for (int lev = 0; lev < 4; ++lev) {
-        if (lev < lev0) continue;                       // bits below lev0 were transformed by the previous sub-stage
+    for (int lev = LEV0; lev < 4; ++lev) {              // levels below LEV0 were transformed by the previous sub-stage
         const int d = 1 << lev;
 #pragma unroll
         for (int r = 0; r < 16; ++r) {
@@ -229,77 +228,105 @@ template <typename T> __device__ __forceinline__ void fwht16(T (&v)[16], int lev
     }
 }
 
-template <typename T> __global__ void __launch_bounds__(512) fwht_fast_kernel(const __grid_constant__ FwhtFastPass p) {
+// sub-stages after the first one, resolved at compile time: the sub-stage starting at bit U covers bits [UU, UU+4) where
+// UU = min(U, B-4) (fewer than four bits left: re-use the top four positions and skip the levels already done)
+template <typename T, int B, int U>
+__device__ __forceinline__ void fwht_sub_chain(T (&v)[16], T *sl, T *gout_t, int q, long long step) {
+    constexpr int UU = (U + 4 > B) ? (B - 4) : U;
+    constexpr int LEV0 = U - UU;
+    const int l = q & ((1 << UU) - 1), h = q >> UU;
+    const int m0 = (h << (UU + 4)) | l;
+    const T *base = sl + m0 + (m0 >> 4);
+    if constexpr (UU >= 4) {
+        // (r << UU) is a multiple of 16: the pad term separates -> immediate offsets
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = base[(r << UU) + ((r << UU) >> 4)];
+    } else {
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { const int m = m0 + (r << UU); v[r] = sl[m + (m >> 4)]; }
+    }
+    fwht16<T, LEV0>(v);
+    if constexpr (UU + 4 >= B) {                        // last sub-stage: straight to global memory
+        T *dst = gout_t + (long long)m0 * step;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) dst[(long long)(r << UU) * step] = v[r];
+    } else {
+        __syncthreads();
+        T *wb = sl + m0 + (m0 >> 4);
+#pragma unroll
+        for (int r = 0; r < 16; ++r) wb[(r << UU) + ((r << UU) >> 4)] = v[r];
+        __syncthreads();
+        fwht_sub_chain<T, B, U + 4>(v, sl, gout_t, q, step);
+    }
+}
+
+template <typename T, int B, bool CONTIG> __global__ void __launch_bounds__(512) fwht_fast_kernel(const __grid_constant__ FwhtFastPass p) {
     extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
     T *sm = reinterpret_cast<T *>(fwht_smem_raw);
     const int tid = threadIdx.x;
-    const int b = p.b, logT = p.logT, Tn = 1 << logT;
-    const int nq = 1 << (b - 4);                        // threads per line
+    const int logT = p.logT, Tn = 1 << logT;
     const long long col = blockIdx.x / p.tiles_per_col;
     const long long tin = blockIdx.x - col * p.tiles_per_col;
-    // tile -> (hi, lo0): the tile covers all 2^b mid values, Tn consecutive lo values starting at lo0, one hi value
+    // tile -> (hi, lo0): the tile covers all 2^B mid values, Tn consecutive lo values starting at lo0, one hi value
     const long long lo_tiles = ((long long)1 << p.s) >> logT;
     const long long hi = tin / lo_tiles, lo0 = (tin - hi * lo_tiles) << logT;
-    const long long base = (hi << (p.s + b)) + lo0;
-    const T *gin = (const T *)p.in + col * p.in_cs + base;
-    T *gout = (T *)p.out + col * p.out_cs + base;
+    const long long base = (hi << (p.s + B)) + lo0;
     const int t = tid & (Tn - 1), q = tid >> logT;      // line-fastest thread order
-    const int RSL = (1 << b) + ((1 << b) >> 4) + 1;     // padded line stride in shared memory
+    const T *gin = (const T *)p.in + col * p.in_cs + base + t;
+    T *gout = (T *)p.out + col * p.out_cs + base + t;
+    constexpr int RSL = (1 << B) + ((1 << B) >> 4) + 1; // padded line stride in shared memory (odd -> conflict free)
     T *sl = sm + t * RSL;
+    const long long step = CONTIG ? 1ll : ((long long)1 << p.s);     // CONTIG: first pass (s == 0), unit stride
     T v[16];
-    int u = 0;
     // ---- first sub-stage: bits [0, 4) of mid straight from global memory
-    {
-        const long long step = (long long)1 << p.s;
-        const T *src = gin + (long long)(q << 4) * step + t;
-        if (p.s == 0 && sizeof(T) == 4 && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {   // contiguous: 4 x 128-bit loads
-            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    const T *src = gin + (long long)(q << 4) * step;
+    if (CONTIG && sizeof(T) == 4 && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {   // contiguous: 4 x 128-bit loads
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                float4 f = s4[r];
-                v[4 * r + 0] = reinterpret_cast<T &>(f.x); v[4 * r + 1] = reinterpret_cast<T &>(f.y);
-                v[4 * r + 2] = reinterpret_cast<T &>(f.z); v[4 * r + 3] = reinterpret_cast<T &>(f.w);
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < 16; ++r) v[r] = src[(long long)r * step];
+        for (int r = 0; r < 4; ++r) {
+            float4 f = s4[r];
+            v[4 * r + 0] = reinterpret_cast<T &>(f.x); v[4 * r + 1] = reinterpret_cast<T &>(f.y);
+            v[4 * r + 2] = reinterpret_cast<T &>(f.z); v[4 * r + 3] = reinterpret_cast<T &>(f.w);
         }
-        fwht16<T>(v, 0);
-        u = 4;
-        if (b == 4) {                                   // a single sub-stage: back to global memory directly
-            T *dst = gout + (long long)(q << 4) * step + t;
+    } else {
 #pragma unroll
-            for (int r = 0; r < 16; ++r) dst[(long long)r * step] = v[r];
-            return;
-        }
-#pragma unroll
-        for (int r = 0; r < 16; ++r) { const int m = (q << 4) + r; sl[m + (m >> 4)] = v[r]; }
+        for (int r = 0; r < 16; ++r) v[r] = src[(long long)r * step];
     }
-    __syncthreads();
-    // ---- middle sub-stages in shared memory, last sub-stage to global memory
-    for (;;) {
-        int lev0 = 0;
-        int uu = u;
-        if (u + 4 > b) { uu = b - 4; lev0 = u - uu; }    // fewer than four bits left: re-use the top four, skip done levels
-        const int l = q & ((1 << uu) - 1), h = q >> uu;
-        const int m0 = (h << (uu + 4)) | l;
+    fwht16<T, 0>(v);
+    if constexpr (B == 4) {                             // a single sub-stage: back to global memory directly
+        T *dst = gout + (long long)(q << 4) * step;
 #pragma unroll
-        for (int r = 0; r < 16; ++r) { const int m = m0 + (r << uu); v[r] = sl[m + (m >> 4)]; }
-        fwht16<T>(v, lev0);
-        if (uu + 4 >= b) {                              // last sub-stage
-            const long long step = (long long)1 << p.s;
-            T *dst = gout + (long long)m0 * step + t;
+        for (int r = 0; r < 16; ++r) dst[(long long)r * step] = v[r];
+    } else {
+        T *wb = sl + 17 * q;                            // m = 16 q + r  ->  m + (m >> 4) = 17 q + r
 #pragma unroll
-            for (int r = 0; r < 16; ++r) dst[(long long)(r << uu) * step] = v[r];
-            return;
-        }
+        for (int r = 0; r < 16; ++r) wb[r] = v[r];
         __syncthreads();
-#pragma unroll
-        for (int r = 0; r < 16; ++r) { const int m = m0 + (r << uu); sl[m + (m >> 4)] = v[r]; }
-        __syncthreads();
-        u += 4;
-        (void)nq;
+        fwht_sub_chain<T, B, 4>(v, sl, gout, q, step);
     }
+}
+
+template <typename T> static int fwht_fast_launch(const FwhtFastPass &p, unsigned grid, int threads, size_t smem, cudaStream_t st) {
+#define FMB_FWHT_CASE(BB)                                                                                              \
+    case BB: {                                                                                                         \
+        static int attr_done = 0;                                                                                      \
+        if (!attr_done) {                                                                                              \
+            FMB_CUDA_OK(cudaFuncSetAttribute(fwht_fast_kernel<T, BB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10)); \
+            FMB_CUDA_OK(cudaFuncSetAttribute(fwht_fast_kernel<T, BB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10)); \
+            attr_done = 1;                                                                                             \
+        }                                                                                                              \
+        if (p.s == 0) fwht_fast_kernel<T, BB, true><<<grid, threads, smem, st>>>(p);                                   \
+        else fwht_fast_kernel<T, BB, false><<<grid, threads, smem, st>>>(p);                                           \
+        break;                                                                                                         \
+    }
+    switch (p.b) {
+        FMB_FWHT_CASE(4) FMB_FWHT_CASE(5) FMB_FWHT_CASE(6) FMB_FWHT_CASE(7) FMB_FWHT_CASE(8)
+        FMB_FWHT_CASE(9) FMB_FWHT_CASE(10) FMB_FWHT_CASE(11) FMB_FWHT_CASE(12)
+        default: set_error("FWHT fast path: unsupported pass width %d", p.b); return FMB_ERR_VALUE;
+    }
+#undef FMB_FWHT_CASE
+    FMB_LAUNCH_OK();
+    return FMB_OK;
 }
 
 template <typename T>
@@ -317,14 +344,12 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
         }
     }
     const int tile_elems = (int)std::min<size_t>(8192, std::max<size_t>(512, (size_t)32768 / sizeof(T)));   // <= 512 threads x 16
-    static int attr_done = 0;
-    if (!attr_done) {
-        FMB_CUDA_OK(cudaFuncSetAttribute(fwht_fast_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
-        attr_done = 1;
-    }
     size_t l2 = device_props().l2_bytes ? device_props().l2_bytes : (size_t)100 << 20;
     static const long slab_mb = getenv("FMB_FWHT_SLAB_MB") ? atol(getenv("FMB_FWHT_SLAB_MB")) : 0;
-    size_t budget = slab_mb > 0 ? (size_t)slab_mb << 20 : l2 / 3;
+    // measured on B200: launch gaps over L2-sized slabs cost more than the L2 hits save (29% vs 35% of roofline), so the
+    // slab follows the same 512 MiB budget as the FFT engine
+    size_t budget = slab_mb > 0 ? (size_t)slab_mb << 20 : (size_t)512 << 20;
+    (void)l2;
     int64_t slab = (int64_t)(budget / (((size_t)1 << order) * sizeof(T)));
     if (slab < 1) slab = 1;
     if (bits.size() == 1) slab = M;
@@ -351,8 +376,8 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
             const long long grid = p.tiles_per_col * nc;
             if (grid > 2147483647LL || threads > 512 || threads < 1) { set_error("FWHT fast path: bad geometry"); return FMB_ERR_VALUE; }
             const size_t smem = (size_t)(1 << logT) * ((size_t)(1 << p.b) + ((size_t)(1 << p.b) >> 4) + 1) * sizeof(T);
-            fwht_fast_kernel<T><<<(unsigned)grid, threads, smem, st>>>(p);
-            FMB_LAUNCH_OK();
+            int rc = fwht_fast_launch<T>(p, (unsigned)grid, threads, smem, st);
+            if (rc) return rc;
             s += p.b;
         }
     }

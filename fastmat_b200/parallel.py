@@ -1,0 +1,72 @@
+"""Column-batch data parallelism for the apply path.
+
+Every operator acts column-wise -- ``forward(x)[:, m]`` depends only on ``x[:, m]`` (e.g. fastmat/Hadamard.pyx:180,
+fastmat/core/cmath.pyx:992-997, ``np.fft.fft(axis=0)``) -- so the M columns of a 2-D operand are split into contiguous
+blocks, one per rank (one process per GPU, ``torch.distributed``), and each rank applies its own plan to its own block.
+There is NO collective on the apply path.  Only when the caller wants the assembled result does ``gather_columns`` issue
+one all_gather / gather (NCCL over NVLink on GPUs; gloo in the CPU tests of the host logic).
+"""
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(num_cols, rank, world_size):
+    """Contiguous, balanced column block of ``rank``: the first ``num_cols % world_size`` ranks get one extra column."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad rank / world size")
+    base, extra = divmod(int(num_cols), int(world_size))
+    start = rank * base + min(rank, extra)
+    return start, start + base + (1 if rank < extra else 0)
+
+
+def shard_columns(x, rank=None, world_size=None):
+    """View of this rank's column block of a full (n, M) operand (no copy)."""
+    if rank is None:
+        rank = dist.get_rank()
+    if world_size is None:
+        world_size = dist.get_world_size()
+    if x.ndim != 2:
+        raise ValueError("column sharding needs a 2D operand")
+    a, b = shard_bounds(x.shape[1], rank, world_size)
+    return x[:, a:b]
+
+
+def apply_sharded(matrix, x_local, backward=False):
+    """Apply ``matrix`` to this rank's column block.  No communication."""
+    return matrix.backward(x_local) if backward else matrix.forward(x_local)
+
+
+def gather_columns(y_local, num_cols, dst=None, group=None):
+    """Assemble the (n, num_cols) result from the per-rank column blocks.
+
+    ``dst=None``: every rank gets the full array (all_gather); otherwise only rank ``dst`` does (others return None).
+    Blocks may differ by one column (``shard_bounds``); they travel padded to the widest block.
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    widths = [shard_bounds(num_cols, r, world)[1] - shard_bounds(num_cols, r, world)[0] for r in range(world)]
+    if y_local.ndim != 2 or y_local.shape[1] != widths[rank]:
+        raise ValueError("local block has %s columns, expected %d" % (tuple(y_local.shape), widths[rank]))
+    wmax = max(widths)
+    n = y_local.shape[0]
+    # communicate column-major blocks: (wmax, n) contiguous buffers
+    send = torch.zeros((wmax, n), dtype=y_local.dtype, device=y_local.device)
+    send[:widths[rank]] = y_local.t()
+    is_cplx = send.is_complex()
+    if is_cplx:
+        send = torch.view_as_real(send)         # the backends move real buffers (gloo has no complex types)
+    if dst is None:
+        recv = [torch.empty_like(send) for _ in range(world)]
+        dist.all_gather(recv, send, group=group)
+    else:
+        recv = [torch.empty_like(send) for _ in range(world)] if rank == dst else None
+        dist.gather(send, recv, dst=dst, group=group)
+        if rank != dst:
+            return None
+    out = torch.empty((num_cols, n), dtype=y_local.dtype, device=y_local.device)
+    c0 = 0
+    for r in range(world):
+        blk = torch.view_as_complex(recv[r]) if is_cplx else recv[r]
+        out[c0:c0 + widths[r]] = blk[:widths[r]]
+        c0 += widths[r]
+    return out.t()                      # (n, num_cols), column-major like every result of the apply path
