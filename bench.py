@@ -181,8 +181,9 @@ def run_reference_arm(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': len(t_steps),
         'warmup': min(warm, 1), 'ms_per_step': t * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'complex64 in / complex128 internally (reference Product.pyx:215)', 'data': 'synthetic',
-        'config': {'workload': 'Circulant(N=2^20).forward, complex64 columns, CPU reference on host cores',
-                   'n': N, 'columns_per_step': workers * cols_per_worker, 'layout': 'column-major'},
+        'config': {'workload': 'Circulant(N=2^20).forward, complex64, %d columns per GPU, column-major (fastmat layout)' % COLS,
+                   'n': N, 'columns_per_gpu': COLS, 'sample': sample,
+                   'note': 'reference arm: fastmat CPU implementation (oracle/_ref) on the host cores, bounded column sample per step'},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': kind, 'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -271,12 +272,19 @@ def run_ours(args):
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     info = C._plan.info
 
-    # per-pass share of a step (one extra untimed profiling step, events around each pass would need hooks in the
-    # library; instead time the operator's building blocks separately at the same shape)
+    # per-kernel share of a step and DRAM traffic: from the committed ncu launch list of this same command
+    # (profiles/r1_traffic.json <- profiles/r1_launches_bench_circulant.csv); live numbers above are CUDA events only
+    traffic = None
     kernels = {}
-    if rank == 0 and not args.quick:
-        F = fm.Fourier(N)
-        kernels['fourier_forward_ms'] = timed(lambda: F.forward(x), max(3, steps // 2), 3) if not distributed else None
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+            tj = json.load(f)
+        if cols == COLS:
+            traffic = tj['dram_bytes_per_step']
+        kernels = {k: {'share_of_step_time': v['share_of_step_time'], 'avg_us_under_ncu': v['avg_us']}
+                   for k, v in tj['kernels'].items()}
+    except Exception:
+        pass
     del y
 
     # ---- e2e: host buffers through Matrix.apply_host (H2D + transform + D2H inside the timed region)
@@ -353,9 +361,12 @@ def run_ours(args):
             'e2e': e2e,
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': None, 'peak_source': peak_src,
+                         'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': alg_bytes,
-                         'note': 'operator level: one step = %d launches (3 passes per slab of columns)' % (launches // steps),
+                         'note': ('operator level: algorithmic bytes of one step (2 x 8 B x N per column, SURVEY 8d) / CUDA-event '
+                                  'time of the step; one step = %d launches (3 passes per slab of %d columns); traffic = DRAM '
+                                  'bytes of the same launches from the committed ncu launch list') % (launches // steps, int(info.slab_cols)),
+                         'launches_per_step': launches // steps,
                          'kernels': kernels},
             'cpu_baseline': cpu,
             'extras': extras,
