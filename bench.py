@@ -207,6 +207,8 @@ def run_ours(args):
     distributed = world > 1
     if distributed:
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'       # NCCL prints its version banner on stdout; stdout carries the JSON line only
         dist.init_process_group('nccl', device_id=dev)
 
     def barrier():
