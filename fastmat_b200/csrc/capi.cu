@@ -55,7 +55,8 @@ static int require_device() {
 }
 
 // kernels implemented in the other translation units
-int fwht_apply(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dtype, cudaStream_t st);
+int fwht_apply(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dtype, void *ws,
+               int64_t ws_bytes, cudaStream_t st);
 int diag_apply(const void *d_dev, int dt_d, int64_t n, int conj_d, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
                int64_t ycs, int64_t M, int dt_x, int dt_out, cudaStream_t st);
 int gather_apply(const void *idx_dev, int64_t nsel, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs,
@@ -205,10 +206,11 @@ struct HadamardPlan : PlanBase {
         o->kind = kind; o->num_rows = num_rows; o->num_cols = num_cols; o->inner_size = num_rows; o->passes_fwd = order > 12 ? 2 : 1;
         return FMB_OK;
     }
+    int64_t workspace_bytes(int, int64_t, int, int) const override { return 256; }   // grid-barrier counter of the fused kernel
     int apply(int, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dt_in, int dt_out,
-              void *, int64_t, cudaStream_t st) const override {
+              void *ws, int64_t ws_bytes, cudaStream_t st) const override {
         if (dt_in != dt_out) { set_error("Hadamard: output dtype must equal input dtype (promote(in, int8) = in)"); return FMB_ERR_TYPE; }
-        return fwht_apply(order, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);       // symmetric: backward == forward (:232-239)
+        return fwht_apply(order, x, xrs, xcs, y, yrs, ycs, M, dt_in, ws, ws_bytes, st);   // symmetric: backward == forward (:232-239)
     }
 };
 

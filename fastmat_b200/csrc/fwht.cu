@@ -260,27 +260,33 @@ __device__ __forceinline__ void fwht_sub_chain(T (&v)[16], T *sl, T *gout_t, int
     }
 }
 
-template <typename T, int B, bool CONTIG> __global__ void __launch_bounds__(512) fwht_fast_kernel(const __grid_constant__ FwhtFastPass p) {
-    extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
-    T *sm = reinterpret_cast<T *>(fwht_smem_raw);
-    const int tid = threadIdx.x;
+// One tile of one pass.  A tile is all 2^B "mid" values x Tn lines; a line is a low-bit value (strided passes) or, for the
+// contiguous first pass, one chunk of 2^B consecutive elements.  CG: read through L2 only (fused kernel: the input was
+// written by other SMs earlier in the same launch).
+template <typename T, int B, bool CONTIG, bool CG>
+__device__ __forceinline__ void fwht_tile(const FwhtFastPass &p, long long tile, T *sm, int tid) {
     const int logT = p.logT, Tn = 1 << logT;
-    const long long col = blockIdx.x / p.tiles_per_col;
-    const long long tin = blockIdx.x - col * p.tiles_per_col;
-    // tile -> (hi, lo0): the tile covers all 2^B mid values, Tn consecutive lo values starting at lo0, one hi value
-    const long long lo_tiles = ((long long)1 << p.s) >> logT;
-    const long long hi = tin / lo_tiles, lo0 = (tin - hi * lo_tiles) << logT;
-    const long long base = (hi << (p.s + B)) + lo0;
+    const long long col = tile / p.tiles_per_col;
+    const long long tin = tile - col * p.tiles_per_col;
     const int t = tid & (Tn - 1), q = tid >> logT;      // line-fastest thread order
-    const T *gin = (const T *)p.in + col * p.in_cs + base + t;
-    T *gout = (T *)p.out + col * p.out_cs + base + t;
+    long long base;
+    if (CONTIG) {
+        base = ((tin << logT) + t) << B;                // chunk (tin*Tn + t) of the column
+    } else {
+        // tile -> (hi, lo0): Tn consecutive lo values starting at lo0, one hi value
+        const long long lo_tiles = ((long long)1 << p.s) >> logT;
+        const long long hi = tin / lo_tiles, lo0 = (tin - hi * lo_tiles) << logT;
+        base = (hi << (p.s + B)) + lo0 + t;
+    }
+    const T *gin = (const T *)p.in + col * p.in_cs + base;
+    T *gout = (T *)p.out + col * p.out_cs + base;
     constexpr int RSL = (1 << B) + ((1 << B) >> 4) + 1; // padded line stride in shared memory (odd -> conflict free)
     T *sl = sm + t * RSL;
-    const long long step = CONTIG ? 1ll : ((long long)1 << p.s);     // CONTIG: first pass (s == 0), unit stride
+    const long long step = CONTIG ? 1ll : ((long long)1 << p.s);
     T v[16];
     // ---- first sub-stage: bits [0, 4) of mid straight from global memory
     const T *src = gin + (long long)(q << 4) * step;
-    if (CONTIG && sizeof(T) == 4 && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {   // contiguous: 4 x 128-bit loads
+    if (CONTIG && !CG && sizeof(T) == 4 && (reinterpret_cast<unsigned long long>(src) & 15ull) == 0) {   // 4 x 128-bit loads
         const float4 *s4 = reinterpret_cast<const float4 *>(src);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
@@ -290,7 +296,7 @@ template <typename T, int B, bool CONTIG> __global__ void __launch_bounds__(512)
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = src[(long long)r * step];
+        for (int r = 0; r < 16; ++r) v[r] = CG ? __ldcg(src + (long long)r * step) : src[(long long)r * step];
     }
     fwht16<T, 0>(v);
     if constexpr (B == 4) {                             // a single sub-stage: back to global memory directly
@@ -304,6 +310,71 @@ template <typename T, int B, bool CONTIG> __global__ void __launch_bounds__(512)
         __syncthreads();
         fwht_sub_chain<T, B, 4>(v, sl, gout, q, step);
     }
+}
+
+template <typename T, int B, bool CONTIG> __global__ void __launch_bounds__(512) fwht_fast_kernel(const __grid_constant__ FwhtFastPass p) {
+    extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
+    fwht_tile<T, B, CONTIG, false>(p, (long long)blockIdx.x, reinterpret_cast<T *>(fwht_smem_raw), (int)threadIdx.x);
+}
+
+// ---- both passes of a two-pass transform in ONE persistent launch.  Columns flow through in slabs small enough for the
+// slab to stay in L2 between its first and its second pass: phase k runs pass 1 of slab k and pass 2 of slab k-1 (static
+// tile lists over all co-resident CTAs), phases are separated by a grid-wide barrier (release-increment + relaxed poll of
+// a global counter; pass 2 reads through L2 only, so no L1 invalidation is needed).  HBM then sees every element once
+// in and once out instead of twice.
+struct FwhtFused2 {
+    FwhtFastPass p1, p2;          // in / out for column 0 of slab 0 (p2.in == p2.out == y)
+    long long M;                  // columns
+    int slab_cols, nslabs;
+    unsigned *barrier;
+};
+
+__device__ __forceinline__ void fwht_red_release(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned fwht_ld_relaxed(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T, int B0, int B1> __global__ void __launch_bounds__(512) fwht_fused2_kernel(const __grid_constant__ FwhtFused2 f) {
+    extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
+    T *sm = reinterpret_cast<T *>(fwht_smem_raw);
+    const int tid = threadIdx.x;
+    for (int ph = 0; ph <= f.nslabs; ++ph) {
+        const long long c1 = (long long)ph * f.slab_cols, c2 = (long long)(ph - 1) * f.slab_cols;
+        const long long n1 = (ph < f.nslabs) ? (f.M - c1 < f.slab_cols ? f.M - c1 : f.slab_cols) * f.p1.tiles_per_col : 0;
+        const long long n2 = (ph >= 1) ? (f.M - c2 < f.slab_cols ? f.M - c2 : f.slab_cols) * f.p2.tiles_per_col : 0;
+        for (long long idx = blockIdx.x; idx < n1 + n2; idx += gridDim.x) {
+            if (idx < n1) fwht_tile<T, B0, true, false>(f.p1, c1 * f.p1.tiles_per_col + idx, sm, tid);
+            else fwht_tile<T, B1, false, true>(f.p2, c2 * f.p2.tiles_per_col + (idx - n1), sm, tid);
+            __syncthreads();                            // shared memory is reused by the next tile
+        }
+        // ---- grid barrier
+        __syncthreads();
+        if (tid == 0) {
+            fwht_red_release(f.barrier, 1u);
+            const unsigned target = (unsigned)(ph + 1) * gridDim.x;
+            while (fwht_ld_relaxed(f.barrier) < target) __nanosleep(20);
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T, int B0, int B1>
+static int fwht_fused2_launch(const FwhtFused2 &f, size_t smem, cudaStream_t st) {
+    static int grid_cap = 0;
+    if (!grid_cap) {
+        FMB_CUDA_OK(cudaFuncSetAttribute(fwht_fused2_kernel<T, B0, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        FMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwht_fused2_kernel<T, B0, B1>, 512, smem));
+        if (per_sm < 1) { set_error("fused FWHT kernel does not fit on an SM"); return FMB_ERR_CUDA; }
+        grid_cap = per_sm * device_props().sm_count;     // all CTAs must be resident: they meet at a grid barrier
+    }
+    fwht_fused2_kernel<T, B0, B1><<<grid_cap, 512, smem, st>>>(f);
+    FMB_LAUNCH_OK();
+    return FMB_OK;
 }
 
 template <typename T> static int fwht_fast_launch(const FwhtFastPass &p, unsigned grid, int threads, size_t smem, cudaStream_t st) {
@@ -329,8 +400,46 @@ template <typename T> static int fwht_fast_launch(const FwhtFastPass &p, unsigne
     return FMB_OK;
 }
 
+template <typename T, int B1>
+static int fwht_fused2(int order, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) {
+    static const long slab_mb = getenv("FMB_FWHT_FUSED_SLAB_MB") ? atol(getenv("FMB_FWHT_FUSED_SLAB_MB")) : 32;
+    FwhtFused2 f;
+    memset(&f, 0, sizeof(f));
+    f.M = M;
+    int64_t slab = (int64_t)(((size_t)slab_mb << 20) / (((size_t)1 << order) * sizeof(T)));
+    if (slab < 1) slab = 1;
+    f.slab_cols = (int)std::min<int64_t>(slab, M);
+    f.nslabs = (int)((M + f.slab_cols - 1) / f.slab_cols);
+    f.barrier = (unsigned *)ws;
+    FMB_CUDA_OK(cudaMemsetAsync(ws, 0, 256, st));
+    f.p1.in = x; f.p1.in_cs = xcs; f.p1.out = y; f.p1.out_cs = ycs;
+    f.p1.b = 12; f.p1.s = 0; f.p1.order = order; f.p1.logT = 1;                 // two 4096-element chunks per tile: 512 threads
+    f.p1.tiles_per_col = ((long long)1 << (order - 12)) >> 1;
+    int logT2 = 0;
+    while ((16 * 512 >> B1) > (1 << logT2)) ++logT2;                            // 512 threads x 16 values / 2^B1 mid values
+    f.p2.in = y; f.p2.in_cs = ycs; f.p2.out = y; f.p2.out_cs = ycs;
+    f.p2.b = B1; f.p2.s = 12; f.p2.order = order; f.p2.logT = logT2;
+    f.p2.tiles_per_col = ((long long)1 << (order - B1)) >> logT2;
+    const size_t e1 = (size_t)2 * ((1 << 12) + (1 << 8) + 1), e2 = ((size_t)1 << logT2) * ((size_t)(1 << B1) + ((size_t)(1 << B1) >> 4) + 1);
+    const size_t smem = std::max(e1, e2) * sizeof(T);
+    return fwht_fused2_launch<T, 12, B1>(f, smem, st);
+}
+
 template <typename T>
-static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, cudaStream_t st) {
+static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes, cudaStream_t st) {
+    // orders 16..20 (12 + 4..8 bits): both passes fused in one persistent launch with the slab resident in L2.  Opt-in:
+    // measured on B200 in round 1 it is correct but slower than two launches over a 512 MiB slab (3.9 ms vs 2.9 ms per
+    // 1024 float32 columns at order 20): ~130 grid barriers cost more than the halved HBM traffic saves.
+    static const long fused_on = getenv("FMB_FWHT_FUSED") ? atol(getenv("FMB_FWHT_FUSED")) : 0;
+    if (fused_on && order >= 16 && order <= 20 && ws != nullptr && ws_bytes >= 256 && M >= 1) {
+        switch (order - 12) {
+            case 4: return fwht_fused2<T, 4>(order, x, xcs, y, ycs, M, ws, st);
+            case 5: return fwht_fused2<T, 5>(order, x, xcs, y, ycs, M, ws, st);
+            case 6: return fwht_fused2<T, 6>(order, x, xcs, y, ycs, M, ws, st);
+            case 7: return fwht_fused2<T, 7>(order, x, xcs, y, ycs, M, ws, st);
+            default: return fwht_fused2<T, 8>(order, x, xcs, y, ycs, M, ws, st);
+        }
+    }
     // bit ranges per pass: a contiguous first pass of up to 12 bits, then strided passes of 4..8 bits
     std::vector<int> bits;
     if (order <= 12) bits.push_back(order);
@@ -385,12 +494,13 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
 }
 
 template <typename T>
-static int fwht_typed(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, cudaStream_t st) {
+static int fwht_typed(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, void *ws,
+                      int64_t ws_bytes, cudaStream_t st) {
     const bool row_major = (xcs == 1 && M > 1);
 #ifndef FMB_EMULATE
     static const long no_fast = getenv("FMB_NO_FAST") ? atol(getenv("FMB_NO_FAST")) : 0;
     if (!no_fast && !row_major && xrs == 1 && yrs == 1 && order >= 8 && order <= 40)
-        return fwht_fast<T>(order, x, xcs, y, ycs, M, st);
+        return fwht_fast<T>(order, x, xcs, y, ycs, M, ws, ws_bytes, st);
 #endif
     // ---- split the bits into passes
     const int tile_bytes = 64 << 10;
@@ -460,16 +570,17 @@ static int fwht_typed(int order, const void *x, int64_t xrs, int64_t xcs, void *
     return FMB_OK;
 }
 
-int fwht_apply(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dtype, cudaStream_t st) {
+int fwht_apply(int order, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dtype, void *ws,
+               int64_t ws_bytes, cudaStream_t st) {
     switch (dtype) {
-        case FMB_INT8: return fwht_typed<int8_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
-        case FMB_INT16: return fwht_typed<int16_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
-        case FMB_INT32: return fwht_typed<int32_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
-        case FMB_INT64: return fwht_typed<int64_t>(order, x, xrs, xcs, y, yrs, ycs, M, st);
-        case FMB_FLOAT32: return fwht_typed<float>(order, x, xrs, xcs, y, yrs, ycs, M, st);
-        case FMB_FLOAT64: return fwht_typed<double>(order, x, xrs, xcs, y, yrs, ycs, M, st);
-        case FMB_COMPLEX64: return fwht_typed<float2>(order, x, xrs, xcs, y, yrs, ycs, M, st);
-        case FMB_COMPLEX128: return fwht_typed<double2>(order, x, xrs, xcs, y, yrs, ycs, M, st);
+        case FMB_INT8: return fwht_typed<int8_t>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
+        case FMB_INT16: return fwht_typed<int16_t>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
+        case FMB_INT32: return fwht_typed<int32_t>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
+        case FMB_INT64: return fwht_typed<int64_t>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
+        case FMB_FLOAT32: return fwht_typed<float>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
+        case FMB_FLOAT64: return fwht_typed<double>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
+        case FMB_COMPLEX64: return fwht_typed<float2>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
+        case FMB_COMPLEX128: return fwht_typed<double2>(order, x, xrs, xcs, y, yrs, ycs, M, ws, ws_bytes, st);
         default: set_error("Hadamard: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
     }
 }

@@ -505,3 +505,55 @@ def test_launches_counted(fm):
     before = fm.launch_count()
     fm.Hadamard(8).forward(torch.ones((256, 4), dtype=torch.float32, device='cuda'))
     assert fm.launch_count() > before
+
+
+# ------------------------------------------------------------------------------------------- opt-in fused kernels
+def _run_with_env(env, code):
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    e = dict(os.environ)
+    e.update(env)
+    r = subprocess.run([sys.executable, '-c', code], cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+_FUSED_CHECK = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import fastmat_b200 as fm
+from oracle import fastmat_oracle as orc
+rng = np.random.default_rng(5)
+def crand(*s): return (rng.standard_normal(s) + 1j * rng.standard_normal(s))
+def dev(a): return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+n = 2 ** 16
+x = crand(n, 5)
+for dt, tol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
+    xd = dev(x.astype(dt))
+    nx = np.linalg.norm(x, axis=0).max() * np.log2(n)
+    F = fm.Fourier(n)
+    assert np.abs(F.forward(xd).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+    assert np.abs(F.backward(xd).cpu().numpy() - orc.fourier_backward(x)).max() / nx < tol
+c = crand(n)
+C = fm.Circulant(c.astype(np.complex64))
+xd = dev(x.astype(np.complex64))
+nc = np.linalg.norm(c) * np.linalg.norm(x, axis=0).max() * np.log2(n)
+assert np.abs(C.forward(xd).cpu().numpy() - orc.circulant_forward(c, x)).max() / nc < 1e-5
+assert np.abs(C.backward(xd).cpu().numpy() - orc.circulant_backward(c, x)).max() / nc < 1e-5
+T = fm.Toeplitz(c[:40000].astype(np.complex64), c[:20000].astype(np.complex64))
+xt = dev(x[:20001].astype(np.complex64))
+assert np.abs(T.forward(xt).cpu().numpy() - orc.toeplitz_forward(c[:40000], c[:20000], x[:20001])).max() / nc < 1e-5
+xi = rng.integers(-2 ** 31, 2 ** 31 - 1, size=(2 ** 17, 7)).astype(np.int32)
+assert np.array_equal(fm.Hadamard(17).forward(dev(xi)).cpu().numpy(), orc.hadamard_forward(xi))
+xf = rng.standard_normal((2 ** 16, 3)).astype(np.float32)
+assert np.array_equal(fm.Hadamard(16).forward(dev(xf)).cpu().numpy(), orc.hadamard_forward(xf))
+print('fused ok', fm.launch_count())
+'''
+
+
+def test_fused_persistent_kernels_opt_in(fm):
+    """The opt-in single-launch pipelines (FMB_FUSED=1: FFT / convolution, FMB_FWHT_FUSED=1: Hadamard) stay correct."""
+    out = _run_with_env({'FMB_FUSED': '1', 'FMB_FWHT_FUSED': '1'}, _FUSED_CHECK)
+    assert 'fused ok' in out
