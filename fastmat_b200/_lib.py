@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'lib', 'libfastmat_b200.so')
+LIB_PATH = os.environ.get('FMB_LIB_PATH') or os.path.join(_HERE, 'lib', 'libfastmat_b200.so')   # override: A/B experiments
 
 FMB_OK, FMB_ERR_VALUE, FMB_ERR_TYPE, FMB_ERR_CUDA, FMB_ERR_NOTIMPL, FMB_ERR_WORKSPACE = 0, -1, -2, -3, -4, -5
 FORWARD, BACKWARD = 0, 1

@@ -23,6 +23,11 @@ static int launch_fft_kernel(const PassParams<double2> &p, bool pow2, unsigned t
     return pow2 ? launch_fft_f64_pow2(p, tiles, nt, smem, st) : launch_fft_f64_gen(p, tiles, nt, smem, st);
 }
 
+static long env_long(const char *name, long dflt) {
+    const char *v = getenv(name);
+    return v ? atol(v) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------- shape planning
 int64_t next_pow2(int64_t v) {
     int64_t p = 1;
@@ -85,6 +90,8 @@ bool plan_shape(int64_t L, FftShape &s) {
         int lg = 0;
         while (((int64_t)1 << lg) < L) ++lg;
         R1 = (int64_t)1 << (lg / 2);
+        static const long split1 = env_long("FMB_SPLIT_LOG1", 0);      // experiments: log2 of the first pass length
+        if (split1 >= 8 && split1 <= 12 && lg - split1 >= 8 && lg - split1 <= 12) R1 = (int64_t)1 << split1;
         R2 = L / R1;
     } else {
         std::sort(primes.begin(), primes.end(), [](int a, int b) { return a > b; });
@@ -157,6 +164,28 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
         int rc = upload_cvec<C>(d.wR[g], w);
         if (rc) return rc;
     }
+    if (shape.npass == 2 && shape.pow2) {
+        // fast path (fft_fast.cuh): per-stage twiddle tables of a pass length R = 16 * 16 * P2, pairs (r = 2p, 2p+1),
+        // butterfly index fastest:  stage 2 (Ns = 16, radix 16) then stage 3 (Ns = 256, radix P2)
+        for (int g = 0; g < 2; ++g) {
+            const int64_t Rg = shape.g[g].R;
+            if (Rg < 256 || Rg > 4096) continue;
+            const long double tp = 6.283185307179586476925286766559005768L;
+            auto root = [&](int64_t e, int64_t n) {
+                e %= n;
+                long double a = tp * (long double)e / (long double)n;
+                return cd((double)cosl(a), (double)-sinl(a));
+            };
+            w.clear();
+            for (int p2 = 0; p2 < 8; ++p2)
+                for (int kk = 0; kk < 16; ++kk) { w.push_back(root(kk * 2 * p2, 256)); w.push_back(root(kk * (2 * p2 + 1), 256)); }
+            const int P2 = (int)(Rg / 256);
+            for (int p2 = 0; p2 < P2 / 2; ++p2)
+                for (int kk = 0; kk < 256; ++kk) { w.push_back(root((int64_t)kk * 2 * p2, Rg)); w.push_back(root((int64_t)kk * (2 * p2 + 1), Rg)); }
+            int rc = upload_cvec<C>(d.twF[g], w);
+            if (rc) return rc;
+        }
+    }
     if (shape.npass == 2 && kron_a == 0) {
         int lg = 0;
         while (((int64_t)1 << (2 * lg)) < L) ++lg;       // B = 2^lg >= sqrt(L)
@@ -179,35 +208,90 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
     int rc;
     if (!pre.empty() && (rc = upload_cvec<C>(d.pre, pre))) return rc;
     if (!post.empty() && (rc = upload_cvec<C>(d.post, post))) return rc;
-    if (!mid.empty() && (rc = upload_cvec<C>(d.mid, mid))) return rc;
+    if (!mid.empty()) {
+        if (shape.npass == 2) {
+            // two-pass convolutions read the spectrum in the middle pass, whose lines are k1 and whose transform index is
+            // k2 (X index k1 + R1 k2): store it transposed, midT[k1*R2 + k2], so that those reads are contiguous
+            const int64_t R1 = shape.g[0].R, R2 = shape.g[1].R;
+            std::vector<cd> mt(mid.size());
+            for (int64_t k2 = 0; k2 < R2; ++k2)
+                for (int64_t k1 = 0; k1 < R1; ++k1) mt[(size_t)(k1 * R2 + k2)] = mid[(size_t)(k2 * R1 + k1)];
+            if ((rc = upload_cvec<C>(d.mid, mt))) return rc;
+        } else if ((rc = upload_cvec<C>(d.mid, mid))) return rc;
+    }
     d.ready = true;
     return FMB_OK;
 }
 
-static long env_long(const char *name, long dflt) {
-    const char *v = getenv(name);
-    return v ? atol(v) : dflt;
+// Columns pushed through all passes together, and how many such slabs are in flight on different streams.
+//  * default for the fast path ("pipelined slabs"): slabs of a few columns whose intermediate stays in the 126 MB L2
+//    between the passes, issued round-robin on `ns` internal streams so that the tail of one launch overlaps the head of
+//    the next; HBM then sees only x and y (FMB_PIPE_STREAMS / FMB_PIPE_MB tune it, FMB_PIPE_STREAMS=1 switches it off);
+//  * otherwise one launch per pass over a 512 MiB slab (FMB_SLAB_MB), intermediate through HBM.
+void ConvEngine::slab_plan(int64_t M, size_t csize, bool fast, int &cols, int &ns) const {
+    ns = 1;
+    if (shape.npass == 1) { cols = (int)std::min<int64_t>(M, 1 << 30); return; }
+    static const long slab_mb = env_long("FMB_SLAB_MB", 0), pipe_ns = env_long("FMB_PIPE_STREAMS", 3),
+                      pipe_mb = env_long("FMB_PIPE_MB", 16);
+    const size_t col_bytes = (size_t)L * csize;
+    if (fast && pipe_ns > 1 && slab_mb == 0) {
+        int64_t c = std::max<int64_t>(1, (int64_t)(((size_t)pipe_mb << 20) / col_bytes));
+        if (M >= 2 * c * pipe_ns) { cols = (int)c; ns = (int)std::min<long>(pipe_ns, FMB_MAX_PIPE); return; }
+    }
+    size_t budget = (size_t)512 << 20;
+    if (slab_mb > 0) budget = (size_t)slab_mb << 20;
+    int64_t s = (int64_t)(budget / col_bytes);
+    if (s < 1) s = 1;
+    cols = (int)std::min<int64_t>(s, M);
 }
 
 int ConvEngine::slab_cols(int64_t M, size_t csize) const {
-    if (shape.npass == 1) return (int)std::min<int64_t>(M, 1 << 30);
-    // Columns pushed through all passes together.  Measured on B200 (round 1): launches over few columns (an
-    // L2-sized slab) lose more to launch gaps and partial waves than they gain from the L2-resident intermediate, so
-    // the slab is sized by a workspace budget (512 MiB) instead; FMB_SLAB_MB overrides it for experiments.
-    size_t budget = (size_t)512 << 20;
-    static const long slab_mb = env_long("FMB_SLAB_MB", 0);
-    if (slab_mb > 0) budget = (size_t)slab_mb << 20;
-    int64_t s = (int64_t)(budget / ((size_t)L * csize));
-    if (s < 1) s = 1;
-    return (int)std::min<int64_t>(s, M);
+    int cols, ns;
+    slab_plan(M, csize, false, cols, ns);
+    return cols;
 }
 
 int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
     if (shape.npass == 1) return 0;
     const int64_t generic = (int64_t)slab_cols(M, csize) * L * (int64_t)csize;
-    if (shape.pow2 && kron_a == 0) return std::max(generic, fused_workspace_bytes(M, csize));
+    if (shape.pow2) {
+        int cols, ns;
+        slab_plan(M, csize, true, cols, ns);
+        int64_t w = std::max(generic, (int64_t)cols * ns * L * (int64_t)csize);
+        if (kron_a == 0) w = std::max(w, fused_workspace_bytes(M, csize));
+        return w;
+    }
     return generic;
 }
+
+// internal streams of the pipelined-slab schedule: one set per device, shared by all plans; `mu` serialises the
+// (host-side, asynchronous) issue of one apply so that fork / join events of concurrent callers cannot interleave
+struct StreamPool {
+    std::mutex mu;
+    int device = -1;
+    cudaStream_t s[FMB_MAX_PIPE] = {};
+    cudaEvent_t fork = nullptr, join[FMB_MAX_PIPE] = {};
+    bool ready = false;
+    int ensure() {
+        int dev = 0;
+        FMB_CUDA_OK(cudaGetDevice(&dev));
+        if (ready && dev == device) return FMB_OK;
+        if (ready) {
+            for (int i = 0; i < FMB_MAX_PIPE; ++i) { cudaStreamDestroy(s[i]); cudaEventDestroy(join[i]); }
+            cudaEventDestroy(fork);
+            ready = false;
+        }
+        for (int i = 0; i < FMB_MAX_PIPE; ++i) {
+            FMB_CUDA_OK(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
+            FMB_CUDA_OK(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
+        }
+        FMB_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+        device = dev;
+        ready = true;
+        return FMB_OK;
+    }
+};
+static StreamPool g_pool;
 
 // ------------------------------------------------------------------------------------------- pass construction
 struct TileChoice { int T, NT; size_t smem; int sf, st, psh, pamt; };
@@ -290,10 +374,14 @@ int launch_fast_f32_L8(unsigned opt, const FastArgs<float2> &a, unsigned tiles, 
 int launch_fast_f32_L9(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L10(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L11(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f32_L12(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f64_L8(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f64_L9(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f64_L10(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f64_L11(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 
-static bool fast_has(const float2 *, int logr) { return logr >= 8 && logr <= 11; }
-static bool fast_has(const double2 *, int logr) { return logr == 8; }
+static bool fast_has(const float2 *, int logr) { return logr >= 8 && logr <= 12; }
+static bool fast_has(const double2 *, int logr) { return logr >= 8 && logr <= 11; }
 static int fast_logt(const float2 *, int logr) { return (logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr); }
 static int fast_logt(const double2 *, int logr) { return ((logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr)) - 1; }
 static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
@@ -301,11 +389,17 @@ static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsign
         case 8: return launch_fast_f32_L8(opt, a, tiles, st);
         case 9: return launch_fast_f32_L9(opt, a, tiles, st);
         case 10: return launch_fast_f32_L10(opt, a, tiles, st);
-        default: return launch_fast_f32_L11(opt, a, tiles, st);
+        case 11: return launch_fast_f32_L11(opt, a, tiles, st);
+        default: return launch_fast_f32_L12(opt, a, tiles, st);
     }
 }
-static int fast_launch(int, unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st) {
-    return launch_fast_f64_L8(opt, a, tiles, st);
+static int fast_launch(int logr, unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st) {
+    switch (logr) {
+        case 8: return launch_fast_f64_L8(opt, a, tiles, st);
+        case 9: return launch_fast_f64_L9(opt, a, tiles, st);
+        case 10: return launch_fast_f64_L10(opt, a, tiles, st);
+        default: return launch_fast_f64_L11(opt, a, tiles, st);
+    }
 }
 static int ilog2_host(int64_t v) { int l = 0; while (((int64_t)1 << l) < v) ++l; return l; }
 
@@ -333,10 +427,28 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
     const int R1 = shape.g[0].R, R2 = shape.g[1].R;
     const int l1 = ilog2_host(R1), l2 = ilog2_host(R2);
     const int t1 = fast_logt((const C *)nullptr, l1), t2 = fast_logt((const C *)nullptr, l2);
-    const int64_t slab = slab_cols(M, sizeof(C));
+    int slab_i, ns;
+    slab_plan(M, sizeof(C), true, slab_i, ns);
+    const int64_t slab = slab_i;
     int rc;
-    for (int64_t c0 = 0; c0 < M; c0 += slab) {
+    // pipelined slabs: fork the caller's stream into ns internal streams, slab k runs on stream k % ns over ring slot
+    // k % ns of the workspace, and the caller's stream joins them all at the end (stream-ordered for the caller)
+    std::unique_lock<std::mutex> pool_lock(g_pool.mu, std::defer_lock);
+    if (ns > 1) {
+        pool_lock.lock();
+        if ((rc = g_pool.ensure())) return rc;
+        FMB_CUDA_OK(cudaEventRecord(g_pool.fork, st));
+        for (int i = 0; i < ns; ++i) FMB_CUDA_OK(cudaStreamWaitEvent(g_pool.s[i], g_pool.fork, 0));
+    }
+    const cudaStream_t caller_st = st;
+    void *const ws_base = ws;
+    int64_t slab_idx = 0;
+    for (int64_t c0 = 0; c0 < M; c0 += slab, ++slab_idx) {
         const int64_t nc = std::min(slab, M - c0);
+        if (ns > 1) {
+            st = g_pool.s[slab_idx % ns];
+            ws = (char *)ws_base + (size_t)(slab_idx % ns) * (size_t)slab * (size_t)L * sizeof(C);
+        }
         FastArgs<C> base;
         memset(&base, 0, sizeof(base));
         base.ncols = (int)nc;
@@ -349,14 +461,14 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
             a.out = (C *)ws; a.out_cs = L; a.out_ks = R2; a.out_is = 1;
             a.I = R2; a.logI = l2;
             a.out_n = (int)L; a.out_lk = R2; a.out_li = 1;
-            a.wR = (const C *)d.wR[0].p;
+            a.tw = (const C *)d.twF[0].p;
             if ((rc = fast_launch(l1, bwd ? FV_K_AC_ : FV_B_F_, a, (unsigned)((nc * R2) >> t1), st))) return rc;
             FastArgs<C> b2 = base;                                    // over i2 (contiguous), lines k1
             b2.in = (const C *)ws; b2.in_cs = L; b2.in_fs = 1; b2.in_is = R2;
             b2.out = (C *)y + c0 * ycs; b2.out_cs = ycs; b2.out_ks = 1; b2.out_is = R2;
             b2.I = R1; b2.logI = l1;
             b2.out_n = (int)L; b2.out_lk = 1; b2.out_li = R2;
-            b2.wR = (const C *)d.wR[1].p;
+            b2.tw = (const C *)d.twF[1].p;
             if ((rc = fast_launch(l2, bwd ? FV_K_BC_ : FV_K_B_, b2, (unsigned)((nc * R1) >> t2), st))) return rc;
             continue;
         }
@@ -367,7 +479,7 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
             a.out = (C *)ws; a.out_cs = L; a.out_ks = 1; a.out_is = R1;
             a.I = R2; a.logI = l2;
             a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
-            a.wR = (const C *)d.wR[0].p; a.twS = (const C *)d.twS[0].p;
+            a.tw = (const C *)d.twF[0].p; a.twS = (const C *)d.twS[0].p;
             a.pre = pre_d;
             unsigned opt;
             if (!two_ffts) opt = bwd ? FV_A_FC_ : FV_A_F_;
@@ -382,7 +494,7 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
             a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
             a.I = R1; a.logI = l1;
             a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
-            a.wR = (const C *)d.wR[1].p;
+            a.tw = (const C *)d.twF[1].p;
             if ((rc = fast_launch(l2, bwd ? FV_B_FC_ : FV_B_F_, a, (unsigned)((nc * R1) >> t2), st))) return rc;
         } else {
             {   // ---- pass B': in place on ws; FFT over n2, * spectrum[k*R1 + i], conj, FFT, * W^{ik}
@@ -390,8 +502,8 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
                 a.in = (const C *)ws; a.in_cs = L; a.in_fs = R1; a.in_is = 1;
                 a.out = (C *)ws; a.out_cs = L; a.out_ks = R1; a.out_is = 1;
                 a.I = R1; a.logI = l1;
-                a.mid = (const C *)d.mid.p; a.mid_ks = R1;
-                a.wR = (const C *)d.wR[1].p; a.twS = (const C *)d.twS[1].p;
+                a.mid = (const C *)d.mid.p; a.mid_is = R2;
+                a.tw = (const C *)d.twF[1].p; a.twS = (const C *)d.twS[1].p;
                 if ((rc = fast_launch(l2, bwd ? FV_BMC_ : FV_BM_, a, (unsigned)((nc * R1) >> t2), st))) return rc;
             }
             {   // ---- pass C: length R1 over f = k1 (contiguous in ws rows), lines i = m2 < R2; out y[k*R2 + i]
@@ -401,10 +513,16 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
                 a.I = R2; a.logI = l2;
                 a.out_n = (int)rows_out; a.out_lk = R2; a.out_li = 1;
                 a.post = post_d;
-                a.wR = (const C *)d.wR[0].p;
+                a.tw = (const C *)d.twF[0].p;
                 unsigned opt = post_d ? (bwd ? FV_C_MPC_ : FV_C_MP_) : FV_C_M_;
                 if ((rc = fast_launch(l1, opt, a, (unsigned)((nc * R2) >> t1), st))) return rc;
             }
+        }
+    }
+    if (ns > 1) {
+        for (int i = 0; i < ns; ++i) {
+            FMB_CUDA_OK(cudaEventRecord(g_pool.join[i], g_pool.s[i]));
+            FMB_CUDA_OK(cudaStreamWaitEvent(caller_st, g_pool.join[i], 0));
         }
     }
     return FMB_OK;
@@ -513,7 +631,7 @@ int ConvEngine::run_fused(Dev &d, int direction, const void *x, int64_t xcs, voi
         a.out = ring; a.out_cs = L; a.out_ks = 1; a.out_is = R1;
         a.I = R2; a.logI = l2;
         a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
-        a.wR = (const C *)d.wR[0].p; a.twS = (const C *)d.twS[0].p;
+        a.tw = (const C *)d.twF[0].p; a.twS = (const C *)d.twS[0].p;
         a.pre = pre_d;
         g.pass[0] = a;
         g.tiles[0] = (unsigned)(((int64_t)f.slab_cols * R2) >> lt1);
@@ -525,7 +643,7 @@ int ConvEngine::run_fused(Dev &d, int direction, const void *x, int64_t xcs, voi
         a.out = (C *)y; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
         a.I = R1; a.logI = l1;
         a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
-        a.wR = (const C *)d.wR[1].p;
+        a.tw = (const C *)d.twF[1].p;
         g.pass[1] = a;
         g.tiles[1] = (unsigned)(((int64_t)f.slab_cols * R1) >> lt2);
         variant = bwd ? 1 : 0;
@@ -534,8 +652,8 @@ int ConvEngine::run_fused(Dev &d, int direction, const void *x, int64_t xcs, voi
         a.in = ring; a.in_cs = L; a.in_fs = R1; a.in_is = 1;
         a.out = ring; a.out_cs = L; a.out_ks = R1; a.out_is = 1;
         a.I = R1; a.logI = l1;
-        a.mid = (const C *)d.mid.p; a.mid_ks = R1;
-        a.wR = (const C *)d.wR[1].p; a.twS = (const C *)d.twS[1].p;
+        a.mid = (const C *)d.mid.p; a.mid_is = R2;
+        a.tw = (const C *)d.twF[1].p; a.twS = (const C *)d.twS[1].p;
         g.pass[1] = a;
         g.tiles[1] = (unsigned)(((int64_t)f.slab_cols * R1) >> lt2);
         FastArgs<C> c = base;
@@ -544,7 +662,7 @@ int ConvEngine::run_fused(Dev &d, int direction, const void *x, int64_t xcs, voi
         c.I = R2; c.logI = l2;
         c.out_n = (int)rows_out; c.out_lk = R2; c.out_li = 1;
         c.post = post_d;
-        c.wR = (const C *)d.wR[0].p;
+        c.tw = (const C *)d.twF[0].p;
         g.pass[2] = c;
         g.tiles[2] = (unsigned)(((int64_t)f.slab_cols * R2) >> lt1);
         variant = pre_d ? (bwd ? 5 : 4) : (bwd ? 3 : 2);
@@ -586,13 +704,17 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
 
     // ---------------- two shared-memory passes per transform, slab by slab over an L2-resident intermediate
     const int64_t slab = slab_cols(M, sizeof(C));
+    if (fast_ok<C>(xrs, yrs, in_real)) {
+        if (ws == nullptr || ws_bytes < workspace_bytes(M, sizeof(C))) {
+            set_error("workspace too small: need %lld bytes", (long long)workspace_bytes(M, sizeof(C)));
+            return FMB_ERR_WORKSPACE;
+        }
+        if (fused_ok<C>()) return run_fused<C>(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
+        return run_fast<C>(d, direction, x, xcs, y, ycs, M, ws, st);
+    }
     if (ws_bytes < slab * L * (int64_t)sizeof(C) || ws == nullptr) {
         set_error("workspace too small: need %lld bytes", (long long)(slab * L * (int64_t)sizeof(C)));
         return FMB_ERR_WORKSPACE;
-    }
-    if (fast_ok<C>(xrs, yrs, in_real)) {
-        if (fused_ok<C>()) return run_fused<C>(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
-        return run_fast<C>(d, direction, x, xcs, y, ycs, M, ws, st);
     }
     const int64_t R1 = shape.g[0].R, R2 = shape.g[1].R;
     const bool kron = kron_a > 0;
@@ -639,7 +761,7 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
                 p.two_ffts = 1;
                 p.lines_total = nc * R1; p.I = R1; p.ncols = nc; p.line_c_fastest = rowmajor;
                 p.in = ws; p.in_cs = tcs; p.in_rs = trs; p.in_lf = R1; p.in_li = 1; p.in_n = L;
-                p.mid = mid_d; p.mid_conj = bwd; p.mid_lk = R1; p.mid_li = 1;
+                p.mid = mid_d; p.mid_conj = bwd; p.mid_lk = 1; p.mid_li = R2;
                 p.out = ws; p.out_cs = tcs; p.out_rs = trs; p.out_lk = R1; p.out_li = 1; p.out_n = L;
                 p.twL = (const C *)d.twL.p; p.twH = (const C *)d.twH.p; p.tw_shift = d.tw_shift;
                 p.tw_mask = (unsigned)(((int64_t)1 << d.tw_shift) - 1);

@@ -14,6 +14,8 @@
 
 namespace fmb {
 
+constexpr int FMB_MAX_PIPE = 6;      // internal streams of the pipelined-slab schedule
+
 struct PassGeom {
     int R = 0;
     std::vector<int> radix;
@@ -40,7 +42,7 @@ struct ConvEngine {
     FftShape shape;
 
     struct Dev {
-        DevArray wR[2], twL, twH, twS[2], pre, post, mid;
+        DevArray wR[2], twF[2], twL, twH, twS[2], pre, post, mid;
         int tw_shift = 0;
         bool ready = false;
     };
@@ -50,6 +52,7 @@ struct ConvEngine {
     int init(int64_t L_, int64_t n_in_, int64_t n_out_, bool two_ffts_);
     int init_kron(int64_t a, int64_t b);
     int slab_cols(int64_t M, size_t csize) const;
+    void slab_plan(int64_t M, size_t csize, bool fast, int &cols, int &ns) const;
     int64_t workspace_bytes(int64_t M, size_t csize) const;
     int passes() const { return shape.npass == 1 ? 1 : (two_ffts ? 3 : 2); }
 

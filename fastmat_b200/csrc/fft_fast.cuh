@@ -53,12 +53,12 @@ template <typename C> struct FastArgs {
     int ncols;
     int in_n, in_lf, in_li;      // load mask: logical row f*in_lf + i*in_li must be < in_n
     int out_n, out_lk, out_li;   // store mask
-    const C *wR;                 // exp(-2 pi i j / R)
+    const C *tw;                 // stage twiddles of this pass length, see fast_stage_table_size()
     const C *twL, *twH;          // four-step twiddle W_N^e = twL[e & mask] * twH[e >> shift]
     int tw_shift; unsigned tw_mask;
     const C *twS;                // twS[i] = W_N^{(R/16) i}
-    const C *mid;                // spectrum: element (k, i) at mid[k*mid_ks + i]
-    int mid_ks;
+    const C *mid;                // spectrum, transposed at plan creation: element (k, i) at mid[i*mid_is + k]
+    int mid_is;
     const C *pre, *post;         // indexed by logical row
 };
 
@@ -80,35 +80,73 @@ enum : unsigned {
 
 template <typename C> __device__ __forceinline__ C ld_cg(const C *p) { return __ldcg(p); }
 
-// read-only load that the compiler may not hoist across other memory operations: keeps the sixteen spectrum loads of the
-// middle pass from all being issued (and held in registers) before the butterfly that consumes them
-__device__ __forceinline__ float2 ld_nc_pinned(const float2 *p) {
+// read-only load whose position in the instruction stream is kept relative to the other loads of its kind (volatile,
+// but no memory clobber): the spectrum loads of the middle pass are software-pipelined by hand, four values ahead of
+// the butterfly that consumes them, instead of being all hoisted (register pressure) or all exposed (latency)
+__device__ __forceinline__ float2 ld_nc_ordered(const float2 *p) {
     float2 r;
-    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p) : "memory");
+    asm volatile("ld.global.nc.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
     return r;
 }
-__device__ __forceinline__ double2 ld_nc_pinned(const double2 *p) {
+__device__ __forceinline__ double2 ld_nc_ordered(const double2 *p) {
     double2 r;
-    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p) : "memory");
+    asm volatile("ld.global.nc.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
     return r;
+}
+
+// barrier between two phases of a pass.  GROUP: both phases use the row-fastest thread order, in which one line is
+// owned by ROWS consecutive threads in every stage, so only those threads have to meet (a warp-level sync for short
+// lines, a named barrier per line otherwise); the lines of a tile then drift apart and hide each other's latencies.
+template <int ROWS, bool GROUP> __device__ __forceinline__ void fast_sync(int t) {
+    if constexpr (!GROUP) __syncthreads();
+    else if constexpr (ROWS <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(t + 1), "n"(ROWS) : "memory");
+}
+
+// Stage twiddles.  A radix-P stage with Ns finished sub-transforms multiplies input r of butterfly j by
+// W_{Ns P}^{(j mod Ns) r}.  They are tabulated per stage as pairs (r = 2p, 2p+1) with j mod Ns as the fastest index:
+//      table[p * Ns + kk] = { W^{kk 2p}, W^{kk (2p+1)} },   p < P/2, kk < Ns
+// so that a thread fetches two twiddles per 128-bit load and the lanes of a warp (consecutive kk in either thread
+// order) read consecutive addresses.  One pass length R has the tables of its second and third stage back to back.
+template <typename C> struct alignas(2 * sizeof(C)) CPair { C a, b; };
+__device__ __forceinline__ CPair<float2> ldg_pair(const CPair<float2> *p) {
+    const float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+    CPair<float2> r; r.a = make_float2(q.x, q.y); r.b = make_float2(q.z, q.w);
+    return r;
+}
+__device__ __forceinline__ CPair<double2> ldg_pair(const CPair<double2> *p) {
+    CPair<double2> r;
+    r.a = __ldg(reinterpret_cast<const double2 *>(p));
+    r.b = __ldg(reinterpret_cast<const double2 *>(p) + 1);
+    return r;
+}
+template <int LOGR> constexpr int fast_stage_table_offset(int stage) {        // in CPair units; stage 1 or 2
+    return stage == 1 ? 0 : (FastPlan<LOGR>::P1 / 2) * FastPlan<LOGR>::P0;
 }
 
 // one radix-P stage on the sixteen register values of a thread.
 //   v[m] holds position jb + ROWS*m on entry (natural Stockham input order of every stage) and, on exit, the values
-//   are written through `store(k, value)` at their Stockham output positions.
+//   are written through `store(k, value)` at their Stockham output positions.  `tab`: this stage's twiddle table.
 template <typename C, int LOGR, int P, int NS, typename Store>
-__device__ __forceinline__ void fast_butterflies(C (&v)[16], int jb, const C *__restrict__ wR, Store store) {
-    constexpr int R = 1 << LOGR, ROWS = R / 16, NBF = 16 / P, TWS = R / (NS * P);
+__device__ __forceinline__ void fast_butterflies(C (&v)[16], int jb, const CPair<C> *__restrict__ tab, Store store) {
+    constexpr int R = 1 << LOGR, ROWS = R / 16, NBF = 16 / P;
 #pragma unroll
     for (int it = 0; it < NBF; ++it) {
         const int j = jb + it * ROWS;
         C u[P];
 #pragma unroll
         for (int r = 0; r < P; ++r) u[r] = v[it + NBF * r];
-        if (NS > 1) {
-            const int kk = j & (NS - 1);
+        if constexpr (NS > 1) {
+            // j mod Ns: the part contributed by `it` is a compile-time offset when a thread's butterflies stay inside Ns
+            const CPair<C> *tp;
+            if constexpr (NS > ROWS * (NBF - 1)) tp = tab + (jb & (NS - 1)) + ((it * ROWS) & (NS - 1));
+            else tp = tab + (j & (NS - 1));
 #pragma unroll
-            for (int r = 1; r < P; ++r) u[r] = cmul(u[r], __ldg(wR + kk * r * TWS));
+            for (int p2 = 0; p2 < P / 2; ++p2) {
+                const CPair<C> w = ldg_pair(tp + p2 * NS);
+                if (p2 > 0) u[2 * p2] = cmul(u[2 * p2], w.a);
+                u[2 * p2 + 1] = cmul(u[2 * p2 + 1], w.b);
+            }
         }
         if constexpr (P == 2) dft2(u[0], u[1]);
         else if constexpr (P == 4) dft4(u[0], u[1], u[2], u[3]);
@@ -145,6 +183,8 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
     const unsigned i0 = line0 & (unsigned)(a.I - 1);
     C v[16];
     int jb, t;
+    const CPair<C> *const tab1 = reinterpret_cast<const CPair<C> *>(a.tw);
+    const CPair<C> *const tab2 = tab1 + fast_stage_table_offset<LOGR>(2);
 
     // ------------------------------------------------------------------ stage 0: global -> registers -> shared
     fast_thread_pos<LOGR, LOGT, LOAD_T>(tid, jb, t);
@@ -169,11 +209,15 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
             v[m] = val;
         }
         C *sline = smem + t * RS;
-        fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, a.wR, [&](int k, C val, int, int) { sline[k + (k >> 4)] = val; });
-        __syncthreads();
+        fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, tab1, [&](int k, C val, int, int) { sline[k + (k >> 4)] = val; });
     }
 
-    constexpr bool INNER_T = LOAD_T;                       // inner stages keep the load order (any order is conflict free)
+    // inner stages (shared -> shared) always use the row-fastest order: conflict free, and their barriers are per line
+#ifndef FMB_FAST_INNER_T
+#define FMB_FAST_INNER_T 0
+#endif
+    constexpr bool INNER_T = FMB_FAST_INNER_T != 0;
+    constexpr bool G0 = !LOAD_T, GL = !STORE_T, GI = !INNER_T;    // is the first / last / an inner stage row-fastest?
     // ------------------------------------------------------------------ stage 1 (and 2): shared -> shared, or the last stage
     auto load16 = [&](const C *sl, int jb_) {
         const C *b = sl + jb_ + (jb_ >> 4);
@@ -205,7 +249,7 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
 #pragma unroll
             for (int b2 = 1; b2 < NBF; b2 *= 2) sq = cmul(sq, sq);
         }
-        fast_butterflies<C, LOGR, P, NS>(v, jb_, a.wR, [&](int k, C val, int it, int q) {
+        fast_butterflies<C, LOGR, P, NS>(v, jb_, (NS == NS1 ? tab1 : tab2), [&](int k, C val, int it, int q) {
             if (OPT & FO_TWIDDLE) {
                 if (q == 0) {                          // start of butterfly `it`: wcur = wbase * s1^it
                     if (it > 0) wbase = cmul(wbase, s1);
@@ -236,15 +280,17 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
 
     if constexpr (!TWO) {
         if constexpr (PL::S == 2) {
+            fast_sync<ROWS, G0 && GL>(t);
             fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
             load16g(smem + t * RS, jb);
             final_store(jb, t, Tag1());
         } else {
+            fast_sync<ROWS, G0 && GI>(t);
             fast_thread_pos<LOGR, LOGT, INNER_T>(tid, jb, t);
             load16g(smem + t * RS, jb);
-            __syncthreads();
-            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
-            __syncthreads();
+            fast_sync<ROWS, GI>(t);
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, tab1, smem_store(smem + t * RS));
+            fast_sync<ROWS, GL && GI>(t);
             fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
             load16g(smem + t * RS, jb);
             final_store(jb, t, Tag2());
@@ -252,44 +298,63 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
     } else {
         // ---- finish the first transform in shared memory; its last stage multiplies every output X[k] by the spectrum
         //      (and conjugates: the second transform runs the inverse as conj(FFT(conj(.))))
+        if constexpr (PART != 2) fast_sync<ROWS, G0 && GI>(t);
         fast_thread_pos<LOGR, LOGT, INNER_T>(tid, jb, t);
         if constexpr (PART != 2) {
-        const C *mp = a.mid + (i0 + t);
-        auto mid_store = [&](C *sl) {
-            return [sl, mp, &a](int k, C val, int, int) {
-                const C w = __ldg(mp + (long long)k * a.mid_ks);
+        // spectrum values of this thread's sixteen outputs k = jb + ROWS*n', loaded four at a time one batch ahead
+        const C *mp = a.mid + (long long)(i0 + t) * a.mid_is + jb;
+        C mv[2][4];
+        auto mid_issue = [&](int b, auto stage_tag) {
+            constexpr int P = decltype(stage_tag)::P, NBF = 16 / P;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int n = 4 * b + e, it = n / P, q = n % P;
+                mv[b & 1][e] = ld_nc_ordered(mp + ROWS * (it + NBF * q));
+            }
+        };
+        auto mid_store = [&](C *sl, auto stage_tag) {
+            return [sl, &mv, &mid_issue, stage_tag](int k, C val, int it, int q) {
+                constexpr int P = decltype(stage_tag)::P;
+                const int n = it * P + q;
+                if (n % 4 == 0 && n + 4 < 16) mid_issue(n / 4 + 1, stage_tag);
+                const C w = mv[(n / 4) & 1][n % 4];
                 sl[k + (k >> 4)] = cconj((OPT & FO_MID_CONJ) ? cmulc(val, w) : cmul(val, w));
             };
         };
-        load16g(smem + t * RS, jb);
-        __syncthreads();
         if constexpr (PL::S == 2) {
-            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, mid_store(smem + t * RS));
-            __syncthreads();
-        } else {
-            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
-            __syncthreads();
+            mid_issue(0, Tag1());
             load16g(smem + t * RS, jb);
-            __syncthreads();
-            fast_butterflies<C, LOGR, PL::P2, NS2>(v, jb, a.wR, mid_store(smem + t * RS));
-            __syncthreads();
+            fast_sync<ROWS, GI>(t);
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, tab1, mid_store(smem + t * RS, Tag1()));
+            fast_sync<ROWS, GI>(t);
+        } else {
+            load16g(smem + t * RS, jb);
+            fast_sync<ROWS, GI>(t);
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, tab1, smem_store(smem + t * RS));
+            fast_sync<ROWS, GI>(t);
+            mid_issue(0, Tag2());
+            load16g(smem + t * RS, jb);
+            fast_sync<ROWS, GI>(t);
+            fast_butterflies<C, LOGR, PL::P2, NS2>(v, jb, tab2, mid_store(smem + t * RS, Tag2()));
+            fast_sync<ROWS, GI>(t);
         }
         }
         if constexpr (PART != 1) {
         // ---- second transform
         load16g(smem + t * RS, jb);
-        __syncthreads();
-        fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, a.wR, smem_store(smem + t * RS));
-        __syncthreads();
+        fast_sync<ROWS, GI>(t);
+        fast_butterflies<C, LOGR, PL::P0, 1>(v, jb, tab1, smem_store(smem + t * RS));
         if constexpr (PL::S == 2) {
+            fast_sync<ROWS, GL && GI>(t);
             fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
             load16g(smem + t * RS, jb);
             final_store(jb, t, Tag1());
         } else {
+            fast_sync<ROWS, GI>(t);
             load16g(smem + t * RS, jb);
-            __syncthreads();
-            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, a.wR, smem_store(smem + t * RS));
-            __syncthreads();
+            fast_sync<ROWS, GI>(t);
+            fast_butterflies<C, LOGR, PL::P1, NS1>(v, jb, tab1, smem_store(smem + t * RS));
+            fast_sync<ROWS, GL && GI>(t);
             fast_thread_pos<LOGR, LOGT, STORE_T>(tid, jb, t);
             load16g(smem + t * RS, jb);
             final_store(jb, t, Tag2());

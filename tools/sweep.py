@@ -28,7 +28,8 @@ if len(sys.argv) > 2 and sys.argv[2] == 'hadamard':
     sys.exit(0)
 C = fm.Circulant(c); F = fm.Fourier(N)
 tc = timed(lambda: C.forward(x)); tf = timed(lambda: F.forward(x))
+yc = C.forward(x); chk = float(yc.real.double().sum() + 3 * yc.imag.double().sum()); chk2 = float(yc.abs().double().sum())
 gb = 16.0 * N * cols / 1e9
-print("env SLAB_MB=%s TILE=%s WIDE=%s | circ %.2f ms %.0f GB/s (%.1f%%) | fourier %.2f ms %.0f GB/s (%.1f%%)" % (
-    os.environ.get('FMB_SLAB_MB'), os.environ.get('FMB_TILE_ELEMS'), os.environ.get('FMB_WIDE_T'),
+print("env PIPE=%s PIPE_MB=%s chk %.6e %.8e SLAB_MB=%s TILE=%s WIDE=%s | circ %.2f ms %.0f GB/s (%.1f%%) | fourier %.2f ms %.0f GB/s (%.1f%%)" % (
+    os.environ.get('FMB_PIPE_STREAMS'), os.environ.get('FMB_PIPE_MB'), chk, chk2, os.environ.get('FMB_SLAB_MB'), os.environ.get('FMB_TILE_ELEMS'), os.environ.get('FMB_WIDE_T'),
     tc, gb / tc * 1e3, gb / tc * 1e3 / 65.539, tf, gb / tf * 1e3, gb / tf * 1e3 / 65.539))
