@@ -391,7 +391,7 @@ class Matrix(object):
     def getCols(self, idx):
         if np.isscalar(idx):
             return self.getCol(int(idx))
-        idx = torch.as_tensor(np.asarray(idx), device=self._default_device()).long()
+        idx = (idx if isinstance(idx, torch.Tensor) else torch.as_tensor(np.asarray(idx))).to(self._default_device()).long().reshape(-1)
         sel = torch.zeros((self.numCols, idx.numel()), dtype=_t.getTorchType(self._fusedType), device=idx.device)
         sel[idx, torch.arange(idx.numel(), device=idx.device)] = 1
         return self.forward(sel)
@@ -407,7 +407,7 @@ class Matrix(object):
     def getRows(self, idx):
         if np.isscalar(idx):
             return self.getRow(int(idx))
-        idx = torch.as_tensor(np.asarray(idx), device=self._default_device()).long()
+        idx = (idx if isinstance(idx, torch.Tensor) else torch.as_tensor(np.asarray(idx))).to(self._default_device()).long().reshape(-1)
         sel = torch.zeros((self.numRows, idx.numel()), dtype=_t.getTorchType(self._fusedType), device=idx.device)
         sel[idx, torch.arange(idx.numel(), device=idx.device)] = 1
         return self.backward(sel).conj().resolve_conj().t()
@@ -496,27 +496,38 @@ class Matrix(object):
             self._cache['lsv'] = self._getLargestSingularValue()
         return self._cache['lsv']
 
-    def _getLargestSingularValue(self, maxSteps=200, relEps=1e-9):
-        """Power iteration on A^H A on the device (the reference calls scipy svds, fastmat/Matrix.pyx:895-919)."""
+    def _getLargestSingularValue(self, maxSteps=100, relEps=1e-13):
+        """sqrt of the largest eigenvalue of A^H A by Lanczos iteration on the device (full re-orthogonalisation, Ritz
+        value of the small tridiagonal matrix on the host).  The reference calls scipy's ARPACK ``svds(k=1)``
+        (fastmat/Matrix.pyx:895-919) -- the same Krylov method -- on ``scipyLinearOperator``; every step here is one
+        forward and one backward apply through the C-ABI."""
         dev = self._default_device()
         tt = _t.getTorchType(_t.promoteTypes(self._fusedType, _t.TYPE_FLOAT64))
         g = torch.Generator(device=dev)
         g.manual_seed(1234)
-        v = torch.randn(self.numCols, dtype=torch.float64, device=dev, generator=g).to(tt)
-        v = v / torch.linalg.vector_norm(v)
-        sigma = 0.0
-        for _ in range(maxSteps):
-            w = self.backward(self.forward(v))
-            nw = float(torch.linalg.vector_norm(w))
-            if nw == 0.0:
-                return 0.0
-            v = w / nw
-            new = np.sqrt(nw)
-            if abs(new - sigma) <= relEps * new:
-                sigma = new
+        q = torch.randn(self.numCols, dtype=torch.float64, device=dev, generator=g).to(tt)
+        q = q / torch.linalg.vector_norm(q)
+        maxSteps = max(1, min(maxSteps, self.numCols))
+        Q = torch.zeros((maxSteps, self.numCols), dtype=tt, device=dev)
+        alphas, betas = [], []
+        theta = 0.0
+        for j in range(maxSteps):
+            Q[j] = q
+            w = self.backward(self.forward(q)).to(tt)
+            alphas.append(float(torch.real(torch.vdot(q, w))))
+            # full re-orthogonalisation against the whole Krylov basis (twice is enough)
+            for _ in range(2):
+                w = w - (Q[:j + 1].conj() @ w) @ Q[:j + 1]
+            beta = float(torch.linalg.vector_norm(w))
+            T = np.diag(alphas) + np.diag(betas, 1) + np.diag(betas, -1)
+            new = float(np.linalg.eigvalsh(T)[-1])
+            done = j >= 2 and abs(new - theta) <= relEps * abs(new)
+            theta = new
+            if done or beta <= 1e-14 * max(abs(theta), 1e-300) or j + 1 == maxSteps:
                 break
-            sigma = new
-        return sigma
+            betas.append(beta)
+            q = w / beta
+        return float(np.sqrt(max(theta, 0.0)))
 
     def reference(self):
         """Dense reference of the matrix, built without the fast transform where a class overrides _reference."""

@@ -21,6 +21,7 @@ from .Permutation import Permutation                               # noqa: F401
 from .Eye import Eye                                               # noqa: F401
 from .Zero import Zero                                             # noqa: F401
 from . import core                                                 # noqa: F401
+from . import algorithms                                           # noqa: F401
 
 __version__ = '0.1.0'
 

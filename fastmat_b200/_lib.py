@@ -41,6 +41,7 @@ SIGNATURES = {
                                       ctypes.c_int, c_vp, c_i64, c_vp]),
     'fmb_plan_destroy': (ctypes.c_int, [c_vp]),
     'fmb_conjugate': (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]),
+    'fmb_ista_step': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int, c_vp]),
     'fmb_cast': (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_i64, c_i64, ctypes.c_int, c_i64, c_i64, c_vp]),
     'fmb_launch_count': (c_i64, []),
 }

@@ -64,6 +64,8 @@ int gather_apply(const void *idx_dev, int64_t nsel, const void *x, int64_t xrs, 
 int scatter_apply(const void *idx_dev, int64_t nsel, int64_t ntotal, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
                   int64_t ycs, int64_t M, int dtype, cudaStream_t st);
 int conj_apply(const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t n, int64_t M, int dtype, cudaStream_t st);
+int ista_step_apply(const void *x, const void *grad, void *step_out, void *x_out, int64_t count, double numL, double alpha, int dtype,
+                    cudaStream_t st);
 int cast_apply(const void *x, int64_t xrs, int64_t xcs, int dt_x, void *y, int64_t yrs, int64_t ycs, int dt_out, int64_t n, int64_t M,
                cudaStream_t st);
 
@@ -397,6 +399,13 @@ int fmb_cast(const void *x, int64_t x_row_stride, int64_t x_col_stride, int dtyp
              int64_t y_col_stride, int dtype_out, int64_t n, int64_t M, void *cuda_stream) {
     FMB_GUARD_BEGIN
     return cast_apply(x, x_row_stride, x_col_stride, dtype_in, y, y_row_stride, y_col_stride, dtype_out, n, M, (cudaStream_t)cuda_stream);
+    FMB_GUARD_END
+}
+
+int fmb_ista_step(const void *x, const void *grad, void *step_out, void *x_out, int64_t count, double num_l, double alpha, int dtype,
+                  void *cuda_stream) {
+    FMB_GUARD_BEGIN
+    return ista_step_apply(x, grad, step_out, x_out, count, num_l, alpha, dtype, (cudaStream_t)cuda_stream);
     FMB_GUARD_END
 }
 

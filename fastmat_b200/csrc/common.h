@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -111,6 +112,19 @@ struct DeviceProps {
     bool ok = false;
 };
 const DeviceProps &device_props();
+
+// ---- pipelined-slab schedule: an apply whose columns are processed slab by slab (several launches per slab, the
+// intermediate of a slab resident in L2) forks the caller's stream into up to FMB_MAX_PIPE internal streams, issues slab
+// k on stream(k), and joins them back, so that consecutive slabs overlap and the caller still sees stream order.
+constexpr int FMB_MAX_PIPE = 6;
+struct PipeScope {
+    std::unique_lock<std::mutex> lock;
+    int ns = 1;
+    cudaStream_t caller = nullptr;
+    int begin(int ns_, cudaStream_t st);
+    cudaStream_t stream(int64_t k) const;
+    int end();
+};
 
 // ---- planner (planner.cpp): fastmat/core/cmath.pyx:35-214
 int64_t find_optimal_fft_size(int64_t order, int max_stage);

@@ -240,4 +240,64 @@ int cast_apply(const void *x, int64_t xrs, int64_t xcs, int dt_x, void *y, int64
     return FMB_OK;
 }
 
+// ---- fused proximal-gradient update of ISTA / FISTA (fastmat/algorithms/ISTA.py:113-123, :150-158):
+//          step = x - numL * grad                      (grad == nullptr: step = x, a plain soft threshold)
+//          m    = max(|step| - alpha, 0)
+//          xnew = m / (m + alpha) * step
+// one read of x and grad, one write of step (optional) and xnew, instead of the reference's seven array sweeps.
+template <typename S> struct IstaAbs {
+    static __device__ __forceinline__ S of(S v) { return fabs(v); }
+    static __device__ __forceinline__ S scale(S v, S f) { return v * f; }
+    static __device__ __forceinline__ S axpy(S x, S a, S g) { return x - a * g; }
+};
+template <> struct IstaAbs<float2> {
+    static __device__ __forceinline__ float of(float2 v) { return hypotf(v.x, v.y); }
+    static __device__ __forceinline__ float2 scale(float2 v, float f) { return make_float2(v.x * f, v.y * f); }
+    static __device__ __forceinline__ float2 axpy(float2 x, float a, float2 g) { return make_float2(x.x - a * g.x, x.y - a * g.y); }
+};
+template <> struct IstaAbs<double2> {
+    static __device__ __forceinline__ double of(double2 v) { return hypot(v.x, v.y); }
+    static __device__ __forceinline__ double2 scale(double2 v, double f) { return make_double2(v.x * f, v.y * f); }
+    static __device__ __forceinline__ double2 axpy(double2 x, double a, double2 g) { return make_double2(x.x - a * g.x, x.y - a * g.y); }
+};
+template <typename V, typename S>
+__global__ void __launch_bounds__(256) ista_step_kernel(const V *__restrict__ x, const V *__restrict__ grad, V *__restrict__ step_out,
+                                                        V *__restrict__ x_out, long long count, S numL, S alpha) {
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < count; e += (long long)gridDim.x * blockDim.x) {
+        V s = x[e];
+        if (grad != nullptr) s = IstaAbs<V>::axpy(s, numL, grad[e]);
+        if (step_out != nullptr) step_out[e] = s;
+        const S m = fmax(IstaAbs<V>::of(s) - alpha, (S)0);
+        x_out[e] = IstaAbs<V>::scale(s, m / (m + alpha));
+    }
+}
+
+int ista_step_apply(const void *x, const void *grad, void *step_out, void *x_out, int64_t count, double numL, double alpha, int dtype,
+                    cudaStream_t st) {
+#ifdef FMB_EMULATE
+    set_error("element-wise kernels are not emulated");
+    return FMB_ERR_NOTIMPL;
+#else
+    if (count <= 0) return FMB_OK;
+    const unsigned grid = ew_grid(count);
+    switch (dtype) {
+        case FMB_FLOAT32:
+            ista_step_kernel<float, float><<<grid, 256, 0, st>>>((const float *)x, (const float *)grad, (float *)step_out, (float *)x_out, count, (float)numL, (float)alpha);
+            break;
+        case FMB_FLOAT64:
+            ista_step_kernel<double, double><<<grid, 256, 0, st>>>((const double *)x, (const double *)grad, (double *)step_out, (double *)x_out, count, numL, alpha);
+            break;
+        case FMB_COMPLEX64:
+            ista_step_kernel<float2, float><<<grid, 256, 0, st>>>((const float2 *)x, (const float2 *)grad, (float2 *)step_out, (float2 *)x_out, count, (float)numL, (float)alpha);
+            break;
+        case FMB_COMPLEX128:
+            ista_step_kernel<double2, double><<<grid, 256, 0, st>>>((const double2 *)x, (const double2 *)grad, (double2 *)step_out, (double2 *)x_out, count, numL, alpha);
+            break;
+        default: set_error("ista_step: unsupported dtype %d (float32/64, complex64/128)", dtype); return FMB_ERR_TYPE;
+    }
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+#endif
+}
+
 }  // namespace fmb

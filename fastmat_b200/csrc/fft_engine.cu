@@ -155,6 +155,13 @@ static void unit_roots(int64_t n, int64_t count, int64_t stride, std::vector<cd>
     }
 }
 
+static cd unit_root(int64_t e, int64_t n) {      // exp(-2 pi i e / n)
+    const long double tp = 6.283185307179586476925286766559005768L;
+    e %= n;
+    long double a = tp * (long double)e / (long double)n;
+    return cd((double)cosl(a), (double)-sinl(a));
+}
+
 template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
     std::lock_guard<std::mutex> lock(mu);
     if (d.ready) return FMB_OK;
@@ -170,12 +177,7 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
         for (int g = 0; g < 2; ++g) {
             const int64_t Rg = shape.g[g].R;
             if (Rg < 256 || Rg > 4096) continue;
-            const long double tp = 6.283185307179586476925286766559005768L;
-            auto root = [&](int64_t e, int64_t n) {
-                e %= n;
-                long double a = tp * (long double)e / (long double)n;
-                return cd((double)cosl(a), (double)-sinl(a));
-            };
+            auto root = unit_root;
             w.clear();
             for (int p2 = 0; p2 < 8; ++p2)
                 for (int kk = 0; kk < 16; ++kk) { w.push_back(root(kk * 2 * p2, 256)); w.push_back(root(kk * (2 * p2 + 1), 256)); }
@@ -264,8 +266,9 @@ int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
     return generic;
 }
 
-// internal streams of the pipelined-slab schedule: one set per device, shared by all plans; `mu` serialises the
-// (host-side, asynchronous) issue of one apply so that fork / join events of concurrent callers cannot interleave
+// internal streams of the pipelined-slab schedule (common.h: PipeScope): one set per device, shared by all plans; `mu`
+// serialises the (host-side, asynchronous) issue of one apply so that fork / join events of concurrent callers cannot
+// interleave
 struct StreamPool {
     std::mutex mu;
     int device = -1;
@@ -292,6 +295,28 @@ struct StreamPool {
     }
 };
 static StreamPool g_pool;
+
+int PipeScope::begin(int ns_, cudaStream_t st) {
+    caller = st;
+    ns = std::max(1, std::min(ns_, (int)FMB_MAX_PIPE));
+    if (ns == 1) return FMB_OK;
+    lock = std::unique_lock<std::mutex>(g_pool.mu);
+    int rc = g_pool.ensure();
+    if (rc) return rc;
+    FMB_CUDA_OK(cudaEventRecord(g_pool.fork, st));
+    for (int i = 0; i < ns; ++i) FMB_CUDA_OK(cudaStreamWaitEvent(g_pool.s[i], g_pool.fork, 0));
+    return FMB_OK;
+}
+cudaStream_t PipeScope::stream(int64_t k) const { return ns > 1 ? g_pool.s[k % ns] : caller; }
+int PipeScope::end() {
+    if (ns == 1) return FMB_OK;
+    for (int i = 0; i < ns; ++i) {
+        FMB_CUDA_OK(cudaEventRecord(g_pool.join[i], g_pool.s[i]));
+        FMB_CUDA_OK(cudaStreamWaitEvent(caller, g_pool.join[i], 0));
+    }
+    lock.unlock();
+    return FMB_OK;
+}
 
 // ------------------------------------------------------------------------------------------- pass construction
 struct TileChoice { int T, NT; size_t smem; int sf, st, psh, pamt; };
@@ -433,20 +458,14 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
     int rc;
     // pipelined slabs: fork the caller's stream into ns internal streams, slab k runs on stream k % ns over ring slot
     // k % ns of the workspace, and the caller's stream joins them all at the end (stream-ordered for the caller)
-    std::unique_lock<std::mutex> pool_lock(g_pool.mu, std::defer_lock);
-    if (ns > 1) {
-        pool_lock.lock();
-        if ((rc = g_pool.ensure())) return rc;
-        FMB_CUDA_OK(cudaEventRecord(g_pool.fork, st));
-        for (int i = 0; i < ns; ++i) FMB_CUDA_OK(cudaStreamWaitEvent(g_pool.s[i], g_pool.fork, 0));
-    }
-    const cudaStream_t caller_st = st;
+    PipeScope pipe;
+    if ((rc = pipe.begin(ns, st))) return rc;
     void *const ws_base = ws;
     int64_t slab_idx = 0;
     for (int64_t c0 = 0; c0 < M; c0 += slab, ++slab_idx) {
         const int64_t nc = std::min(slab, M - c0);
         if (ns > 1) {
-            st = g_pool.s[slab_idx % ns];
+            st = pipe.stream(slab_idx);
             ws = (char *)ws_base + (size_t)(slab_idx % ns) * (size_t)slab * (size_t)L * sizeof(C);
         }
         FastArgs<C> base;
@@ -519,12 +538,7 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
             }
         }
     }
-    if (ns > 1) {
-        for (int i = 0; i < ns; ++i) {
-            FMB_CUDA_OK(cudaEventRecord(g_pool.join[i], g_pool.s[i]));
-            FMB_CUDA_OK(cudaStreamWaitEvent(caller_st, g_pool.join[i], 0));
-        }
-    }
+    if ((rc = pipe.end())) return rc;
     return FMB_OK;
 #endif
 }

@@ -14,8 +14,6 @@
 
 namespace fmb {
 
-constexpr int FMB_MAX_PIPE = 6;      // internal streams of the pipelined-slab schedule
-
 struct PassGeom {
     int R = 0;
     std::vector<int> radix;

@@ -455,15 +455,35 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
     const int tile_elems = (int)std::min<size_t>(8192, std::max<size_t>(512, (size_t)32768 / sizeof(T)));   // <= 512 threads x 16
     size_t l2 = device_props().l2_bytes ? device_props().l2_bytes : (size_t)100 << 20;
     static const long slab_mb = getenv("FMB_FWHT_SLAB_MB") ? atol(getenv("FMB_FWHT_SLAB_MB")) : 0;
-    // measured on B200: launch gaps over L2-sized slabs cost more than the L2 hits save (29% vs 35% of roofline), so the
-    // slab follows the same 512 MiB budget as the FFT engine
-    size_t budget = slab_mb > 0 ? (size_t)slab_mb << 20 : (size_t)512 << 20;
+    static const long pipe_ns = getenv("FMB_FWHT_PIPE_STREAMS") ? atol(getenv("FMB_FWHT_PIPE_STREAMS")) : 3;
+    static const long pipe_mb = getenv("FMB_FWHT_PIPE_MB") ? atol(getenv("FMB_FWHT_PIPE_MB")) : 16;
+    // Multi-pass orders: "pipelined slabs" (common.h: PipeScope) - slabs of a few columns whose intermediate (y itself:
+    // the passes after the first work in place) is still in L2 when the next pass reads it, issued round-robin on
+    // internal streams so that launch gaps and partial waves of one slab are filled by the next.  Fallback (few columns,
+    // or FMB_FWHT_PIPE_STREAMS=1): one launch per pass over a 512 MiB slab.
     (void)l2;
-    int64_t slab = (int64_t)(budget / (((size_t)1 << order) * sizeof(T)));
-    if (slab < 1) slab = 1;
+    const size_t col_bytes = ((size_t)1 << order) * sizeof(T);
+    int ns = 1;
+    int64_t slab;
+    {
+        size_t budget = slab_mb > 0 ? (size_t)slab_mb << 20 : (size_t)512 << 20;
+        slab = (int64_t)(budget / col_bytes);
+        if (slab < 1) slab = 1;
+        if (bits.size() > 1 && pipe_ns > 1 && slab_mb == 0) {
+            int64_t c = std::max<int64_t>(1, (int64_t)(((size_t)pipe_mb << 20) / col_bytes));
+            if (M >= 2 * c * pipe_ns) { slab = c; ns = (int)pipe_ns; }
+        }
+    }
     if (bits.size() == 1) slab = M;
-    for (int64_t c0 = 0; c0 < M; c0 += slab) {
+    PipeScope pipe;
+    {
+        int rc = pipe.begin(ns, st);
+        if (rc) return rc;
+    }
+    int64_t slab_idx = 0;
+    for (int64_t c0 = 0; c0 < M; c0 += slab, ++slab_idx) {
         const int64_t nc = std::min<int64_t>(slab, M - c0);
+        st = pipe.stream(slab_idx);
         int s = 0;
         for (size_t pi = 0; pi < bits.size(); ++pi) {
             FwhtFastPass p;
@@ -490,7 +510,7 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
             s += p.b;
         }
     }
-    return FMB_OK;
+    return pipe.end();
 }
 
 template <typename T>

@@ -36,6 +36,27 @@ def apply_sharded(matrix, x_local, backward=False):
     return matrix.backward(x_local) if backward else matrix.forward(x_local)
 
 
+def share_largest_singular_value(matrix, src=0, group=None):
+    """ISTA / FISTA step size: the power iteration runs on rank ``src`` only and the scalar is broadcast (8 bytes), so
+    that every rank iterates with the identical step size; cached on the matrix like the property itself."""
+    dev = matrix._default_device() if dist.get_backend(group) == 'nccl' else torch.device('cpu')
+    t = torch.zeros(1, dtype=torch.float64, device=dev)
+    if dist.get_rank(group) == src:
+        t[0] = float(matrix.largestSingularValue)
+    dist.broadcast(t, src=src, group=group)
+    matrix._cache['lsv'] = float(t.item())
+    return matrix._cache['lsv']
+
+
+def solve_sharded(algorithm, b_local, share_step_size=True):
+    """Run a fastmat_b200.algorithms solver on this rank's block of right-hand sides (columns are independent problems:
+    no collective inside the iteration).  With ``share_step_size`` the largest singular value is computed once and
+    broadcast first (only ISTA / FISTA need it)."""
+    if share_step_size and dist.is_initialized() and hasattr(algorithm, 'numLambda'):
+        share_largest_singular_value(algorithm.fmatA)
+    return algorithm.process(b_local)
+
+
 def gather_columns(y_local, num_cols, dst=None, group=None):
     """Assemble the (n, num_cols) result from the per-rank column blocks.
 

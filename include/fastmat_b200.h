@@ -136,6 +136,13 @@ int fmb_cast(const void *x, int64_t x_row_stride, int64_t x_col_stride, int dtyp
              void *y, int64_t y_row_stride, int64_t y_col_stride, int dtype_out,
              int64_t n, int64_t M, void *cuda_stream);
 
+/* Fused proximal-gradient update of ISTA / FISTA on `count` contiguous elements (replaces the numpy expression chain of
+ * fastmat/algorithms/ISTA.py:150-158 + softThreshold :113-123):
+ *     step = x - num_l * grad;  m = max(|step| - alpha, 0);  x_out = m / (m + alpha) * step
+ * grad == NULL: step = x (plain soft threshold); step_out == NULL: the step is not stored.  dtype: float32/64, complex64/128. */
+int fmb_ista_step(const void *x, const void *grad, void *step_out, void *x_out, int64_t count,
+                  double num_l, double alpha, int dtype, void *cuda_stream);
+
 /* Count of kernel launches issued by this library in the calling process (for bench.py's gpu_launches). */
 int64_t fmb_launch_count(void);
 
