@@ -6,6 +6,7 @@
 
 #include "fft_fast.cuh"
 #include "fft_fused.cuh"
+#include "fft_v32.cuh"
 #include "fft_pass.cuh"
 
 namespace fmb {
@@ -186,6 +187,19 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
                 for (int kk = 0; kk < 256; ++kk) { w.push_back(root((int64_t)kk * 2 * p2, Rg)); w.push_back(root((int64_t)kk * (2 * p2 + 1), Rg)); }
             int rc = upload_cvec<C>(d.twF[g], w);
             if (rc) return rc;
+            if (Rg == 1024) {
+                // 32-values-per-thread passes (fft_v32.cuh): second-stage twiddles {W_1024^{kk 2p}, W_1024^{kk (2p+1)}} at
+                // [p * 32 + kk], stored twice (see v32_pass_kernel), and the four-step step factor W_L^{32 i}
+                w.clear();
+                for (int copy = 0; copy < 2; ++copy)
+                    for (int p2 = 0; p2 < 16; ++p2)
+                        for (int kk = 0; kk < 32; ++kk) { w.push_back(root(kk * 2 * p2, 1024)); w.push_back(root(kk * (2 * p2 + 1), 1024)); }
+                if ((rc = upload_cvec<C>(d.twV[g], w))) return rc;
+                if (kron_a == 0) {
+                    unit_roots(L, L / Rg, 32, w);
+                    if ((rc = upload_cvec<C>(d.twS32[g], w))) return rc;
+                }
+            }
         }
     }
     if (shape.npass == 2 && kron_a == 0) {
@@ -543,6 +557,124 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
 #endif
 }
 
+// ------------------------------------------------------------------------------------------- V32 path (fft_v32.cuh)
+int launch_v32_a(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_v32_b(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_v32_m(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_v32_c(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+static int launch_v32(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
+    int rc = launch_v32_a(opt, a, tiles, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_b(opt, a, tiles, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_m(opt, a, tiles, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_c(opt, a, tiles, st);
+    if (rc == FMB_ERR_NOTIMPL) set_error("V32 path: unknown pass variant %u", opt);
+    return rc;
+}
+
+bool ConvEngine::v32_ok(size_t csize) const {
+#ifdef FMB_EMULATE
+    return false;
+#else
+    static const long off = env_long("FMB_NO_V32", 0);
+    return !off && csize == sizeof(float2) && shape.npass == 2 && shape.g[0].R == 1024 && shape.g[1].R == 1024;
+#endif
+}
+
+// L = 2^20 = 1024 x 1024, complex64, column-major: the same passes as run_fast with 32 values per thread.  The
+// intermediate is stored [k1][n2] (n2 contiguous), so that the middle pass of a convolution works on contiguous lines.
+int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const {
+#ifdef FMB_EMULATE
+    return FMB_ERR_NOTIMPL;
+#else
+    typedef float2 C;
+    const bool bwd = direction == FMB_BACKWARD;
+    const int64_t rows_in = bwd ? n_out : n_in, rows_out = bwd ? n_in : n_out;
+    const C *pre_d = (const C *)(bwd ? d.post.p : d.pre.p);
+    const C *post_d = (const C *)(bwd ? d.pre.p : d.post.p);
+    const int R1 = 1024, R2 = 1024, l1 = 10, l2 = 10;
+    int slab_i, ns;
+    slab_plan(M, sizeof(C), true, slab_i, ns);
+    const int64_t slab = slab_i;
+    int rc;
+    PipeScope pipe;
+    if ((rc = pipe.begin(ns, st))) return rc;
+    void *const ws_base = ws;
+    int64_t slab_idx = 0;
+    for (int64_t c0 = 0; c0 < M; c0 += slab, ++slab_idx) {
+        const int64_t nc = std::min(slab, M - c0);
+        if (ns > 1) {
+            st = pipe.stream(slab_idx);
+            ws = (char *)ws_base + (size_t)(slab_idx % ns) * (size_t)slab * (size_t)L * sizeof(C);
+        }
+        const unsigned tiles = (unsigned)((nc * 1024) >> V32_LOGT);
+        FastArgs<C> base;
+        memset(&base, 0, sizeof(base));
+        base.ncols = (int)nc;
+        base.twL = (const C *)d.twL.p; base.twH = (const C *)d.twH.p; base.tw_shift = d.tw_shift;
+        base.tw_mask = (unsigned)(((int64_t)1 << d.tw_shift) - 1);
+        base.I = 1024; base.logI = 10;
+        if (kron_a > 0) {
+            FastArgs<C> a = base;                                     // over i1 (stride R2), lines i2; natural order out
+            a.in = (const C *)x + c0 * xcs; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
+            a.out = (C *)ws; a.out_cs = L; a.out_ks = R2; a.out_is = 1;
+            a.out_n = (int)L; a.out_lk = R2; a.out_li = 1;
+            a.tw = (const C *)d.twV[0].p;
+            if ((rc = launch_v32(bwd ? V32_K_AC : V32_K_A, a, tiles, st))) return rc;
+            FastArgs<C> b2 = base;                                    // over i2 (contiguous), lines k1
+            b2.in = (const C *)ws; b2.in_cs = L; b2.in_fs = 1; b2.in_is = R2;
+            b2.out = (C *)y + c0 * ycs; b2.out_cs = ycs; b2.out_ks = 1; b2.out_is = R2;
+            b2.out_n = (int)L; b2.out_lk = 1; b2.out_li = R2;
+            b2.tw = (const C *)d.twV[1].p;
+            if ((rc = launch_v32(bwd ? V32_K_BC : V32_K_B, b2, tiles, st))) return rc;
+            continue;
+        }
+        {   // ---- pass A: length R1 over n = f*R2 + i (lines i contiguous); out ws[k1*R2 + i], times W^{i k1}
+            FastArgs<C> a = base;
+            a.in = (const C *)x + c0 * xcs; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
+            a.out = (C *)ws; a.out_cs = L; a.out_ks = R2; a.out_is = 1;
+            a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
+            a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[0].p;
+            a.pre = pre_d;
+            unsigned opt;
+            if (!two_ffts) opt = bwd ? V32_A_FC : V32_A_F;
+            else if (pre_d) opt = bwd ? V32_A_MPC : V32_A_MP;
+            else opt = (rows_in < L) ? V32_A_M : V32_A_F;
+            if ((rc = launch_v32(opt, a, tiles, st))) return rc;
+        }
+        if (!two_ffts) {
+            // ---- pass B: length R2 over n2 (contiguous in ws), lines k1; out y[k1 + R1 k2]
+            FastArgs<C> a = base;
+            a.in = (const C *)ws; a.in_cs = L; a.in_fs = 1; a.in_is = R2;
+            a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
+            a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
+            a.tw = (const C *)d.twV[1].p;
+            if ((rc = launch_v32(bwd ? V32_B_FC : V32_B_F, a, tiles, st))) return rc;
+        } else {
+            {   // ---- pass B': in place on ws lines k1: FFT over n2, * spectrum[k1][k2], conj, FFT, * W^{k1 m2}
+                FastArgs<C> a = base;
+                a.in = (const C *)ws; a.in_cs = L; a.in_fs = 1; a.in_is = R2;
+                a.out = (C *)ws; a.out_cs = L; a.out_ks = 1; a.out_is = R2;
+                a.mid = (const C *)d.mid.p; a.mid_is = R2;
+                a.tw = (const C *)d.twV[1].p; a.twS = (const C *)d.twS32[1].p;
+                if ((rc = launch_v32(bwd ? V32_BMC : V32_BM, a, tiles, st))) return rc;
+            }
+            {   // ---- pass C: length R1 over k1 (stride R2 in ws), lines m2; conj, post-multiply, truncate; out y[m1*R2 + m2]
+                FastArgs<C> a = base;
+                a.in = (const C *)ws; a.in_cs = L; a.in_fs = R2; a.in_is = 1;
+                a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R2; a.out_is = 1;
+                a.out_n = (int)rows_out; a.out_lk = R2; a.out_li = 1;
+                a.post = post_d;
+                a.tw = (const C *)d.twV[0].p;
+                unsigned opt = post_d ? (bwd ? V32_C_MPC : V32_C_MP) : V32_C_M;
+                if ((rc = launch_v32(opt, a, tiles, st))) return rc;
+            }
+        }
+    }
+    return pipe.end();
+    (void)l1; (void)l2;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------- fused persistent path
 int launch_fused_f32_8_8(int variant, const FusedArgs<float2> &g, cudaStream_t st);
 int launch_fused_f32_8_9(int variant, const FusedArgs<float2> &g, cudaStream_t st);
@@ -724,6 +856,7 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
             return FMB_ERR_WORKSPACE;
         }
         if (fused_ok<C>()) return run_fused<C>(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
+        if (v32_ok(sizeof(C))) return run_v32(d, direction, x, xcs, y, ycs, M, ws, st);
         return run_fast<C>(d, direction, x, xcs, y, ycs, M, ws, st);
     }
     if (ws_bytes < slab * L * (int64_t)sizeof(C) || ws == nullptr) {

@@ -40,7 +40,7 @@ struct ConvEngine {
     FftShape shape;
 
     struct Dev {
-        DevArray wR[2], twF[2], twL, twH, twS[2], pre, post, mid;
+        DevArray wR[2], twF[2], twV[2], twS32[2], twL, twH, twS[2], pre, post, mid;
         int tw_shift = 0;
         bool ready = false;
     };
@@ -63,6 +63,8 @@ struct ConvEngine {
     template <typename C> bool fast_ok(int64_t xrs, int64_t yrs, bool in_real) const;
     template <typename C>
     int run_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const;
+    bool v32_ok(size_t csize) const;
+    int run_v32(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const;
     template <typename C> bool fused_ok() const;
     template <typename C>
     int run_fused(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes,

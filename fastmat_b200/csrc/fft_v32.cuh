@@ -1,0 +1,263 @@
+// "V32" passes: the length-1024 pass of a 2^20-point transform with THIRTY-TWO values per thread.
+//
+// 1024 = 32 * 32: a thread owns the 32 positions jb + 32 m of one line, so a pass is two radix-32 stages with ONE
+// exchange through shared memory (the 16-values-per-thread path of fft_fast.cuh needs 16 * 16 * 4: two exchanges), and
+// because the last stage of one transform leaves thread jb with exactly the positions jb + 32 q that the first stage of
+// the next transform reads, the middle pass of a convolution (FFT -> * spectrum -> conj -> FFT) needs two exchanges
+// instead of five.  A line is owned by one warp in the row-fastest order: the middle pass, whose lines are contiguous
+// in the (transposed) intermediate, contains no CTA-wide barrier at all - only __syncwarp().
+//
+// Shared-memory traffic per point drops from 25 to 15 accesses over the three passes of a Circulant apply; that pipe
+// (128 B/clk/SM) and the issue slots are the two co-limiters of these kernels.
+//
+// Same argument block and option bits as the fast path (FastArgs / FO_*); 256 threads, 8 lines per tile, <= 128
+// registers, 2 CTAs per SM.  complex64 only (complex128 stays on the 16-value path: 32 double2 values do not fit).
+#pragma once
+#include "fft_fast.cuh"
+
+namespace fmb {
+
+constexpr int V32_LOGT = 3, V32_T = 1 << V32_LOGT, V32_NT = 256;
+constexpr int V32_RS = 1058;                   // line stride: 1024 + one pad per 32, == 2 (mod 16) (see fft_fast.cuh)
+constexpr size_t V32_SMEM = (size_t)V32_T * V32_RS * sizeof(float2);
+
+// z * exp(-2 pi i K / 32)
+template <int K, typename C> __device__ __forceinline__ C mul_w32(C z) {
+    typedef typename real_of<C>::type S;
+    if constexpr (K == 0) return z;
+    else if constexpr (K == 8) return cmul_mi(z);
+    else if constexpr (K == 4) { const S h = (S)0.70710678118654752440084436210485; return mk<C>((z.x + z.y) * h, (z.y - z.x) * h); }
+    else if constexpr (K == 12) { const S h = (S)0.70710678118654752440084436210485; return mk<C>((z.y - z.x) * h, -(z.x + z.y) * h); }
+    else {
+        constexpr double ang = 6.283185307179586476925286766559 * K / 32.0;
+        // constexpr cos / sin of the sixteen angles (no constexpr libm in device code): table
+        constexpr double ct[16] = {1.0, 0.98078528040323044912618223613424, 0.92387953251128675612818318939679,
+                                   0.83146961230254523707878837761791, 0.70710678118654752440084436210485,
+                                   0.55557023301960222474283081394853, 0.38268343236508977172845998403040,
+                                   0.19509032201612826784828486847702, 0.0, -0.19509032201612826784828486847702,
+                                   -0.38268343236508977172845998403040, -0.55557023301960222474283081394853,
+                                   -0.70710678118654752440084436210485, -0.83146961230254523707878837761791,
+                                   -0.92387953251128675612818318939679, -0.98078528040323044912618223613424};
+        constexpr double st[16] = {0.0, 0.19509032201612826784828486847702, 0.38268343236508977172845998403040,
+                                   0.55557023301960222474283081394853, 0.70710678118654752440084436210485,
+                                   0.83146961230254523707878837761791, 0.92387953251128675612818318939679,
+                                   0.98078528040323044912618223613424, 1.0, 0.98078528040323044912618223613424,
+                                   0.92387953251128675612818318939679, 0.83146961230254523707878837761791,
+                                   0.70710678118654752440084436210485, 0.55557023301960222474283081394853,
+                                   0.38268343236508977172845998403040, 0.19509032201612826784828486847702};
+        (void)ang;
+        const S c = (S)ct[K], s = (S)st[K];
+        return mk<C>(z.x * c + z.y * s, z.y * c - z.x * s);
+    }
+}
+
+template <typename C, int K> __device__ __forceinline__ void dft32_combine(C (&v)[32], const C (&e)[16], const C (&o)[16]) {
+    if constexpr (K < 16) {
+        constexpr int p = outpos<16>(K);
+        const C t = mul_w32<K>(o[p]);
+        v[K] = cadd(e[p], t);
+        v[K + 16] = csub(e[p], t);
+        dft32_combine<C, K + 1>(v, e, o);
+    }
+}
+
+// forward 32-point DFT in registers, natural order in and out: two radix-16 butterflies on the even / odd inputs and
+// a radix-2 combine  X[k] = E[k] + W32^k O[k],  X[k+16] = E[k] - W32^k O[k]
+template <typename C> __device__ __forceinline__ void dft32(C (&v)[32]) {
+    C e[16], o[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { e[r] = v[2 * r]; o[r] = v[2 * r + 1]; }
+    dft16(e);
+    dft16(o);
+    dft32_combine<C, 0>(v, e, o);
+}
+
+// stage-twiddle pair load that is neither merged with the identical load of the pass's other transform nor hoisted as a
+// block (the compiler would otherwise keep all sixteen pairs - 64 registers - alive across the whole middle pass)
+__device__ __forceinline__ CPair<float2> ldg_pair_ordered(const CPair<float2> *p) {
+    CPair<float2> r;
+    asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.a.x), "=f"(r.a.y), "=f"(r.b.x), "=f"(r.b.y) : "l"(p));
+    return r;
+}
+
+template <bool ORDER_T> __device__ __forceinline__ void v32_pos(int tid, int &jb, int &t) {
+    if (ORDER_T) { t = tid & (V32_T - 1); jb = tid >> V32_LOGT; }
+    else { jb = tid & 31; t = tid >> 5; }
+}
+
+// warp-level barrier if the line stays inside one warp on both sides (row-fastest before and after), else CTA-wide
+template <bool WARP> __device__ __forceinline__ void v32_sync() {
+    if constexpr (WARP) __syncwarp();
+    else __syncthreads();
+}
+
+template <unsigned OPT>
+__global__ void __launch_bounds__(V32_NT, 2) v32_pass_kernel(const __grid_constant__ FastArgs<float2> a) {
+    typedef float2 C;
+    extern __shared__ __align__(16) unsigned char fmb_v32_smem[];
+    C *const smem = reinterpret_cast<C *>(fmb_v32_smem);
+    constexpr bool LOAD_T = (OPT & FO_LOAD_T) != 0, STORE_T = (OPT & FO_STORE_T) != 0, TWO = (OPT & FO_TWO_FFTS) != 0;
+    const int tid = threadIdx.x;
+    const unsigned line0 = blockIdx.x << V32_LOGT;
+    const unsigned col = line0 >> a.logI;                  // 8 divides I: a tile never straddles two columns
+    const unsigned i0 = line0 & (unsigned)(a.I - 1);
+    C v[32];
+    int jb, t;
+
+    // ------------------------------------------------------------------ global -> registers, first radix-32 stage
+    v32_pos<LOAD_T>(tid, jb, t);
+    {
+        const unsigned i = i0 + t;
+        const C *src = a.in + (long long)col * a.in_cs + (long long)i * a.in_is + (long long)jb * a.in_fs;
+        const long long fstep = (long long)32 * a.in_fs;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) {
+            const int f = jb + 32 * m;
+            bool ok = true;
+            if (OPT & FO_IN_MASK) ok = (f * a.in_lf + (int)i * a.in_li) < a.in_n;
+            C val = mk<C>(0, 0);
+            if (ok) {
+                val = LOAD_T ? src[m * fstep] : src[32 * m];          // row-fastest: the transform index is contiguous
+                if (OPT & FO_IN_CONJ) val = cconj(val);
+                if (OPT & FO_PRE) {
+                    const C w = __ldg(a.pre + (f * a.in_lf + (int)i * a.in_li));
+                    val = (OPT & FO_PRE_CONJ) ? cmulc(val, w) : cmul(val, w);
+                }
+            }
+            v[m] = val;
+        }
+    }
+    dft32(v);
+    {
+        C *sl = smem + t * V32_RS + jb * 33;                            // position k = 32 jb + q at k + (k >> 5)
+#pragma unroll
+        for (int q = 0; q < 32; ++q) sl[q] = v[q];
+    }
+
+    const CPair<C> *const tab = reinterpret_cast<const CPair<C> *>(a.tw);
+    // second radix-32 stage: v[m] <- position jb + 32 m, times W_1024^{jb m}, DFT; leaves X[jb + 32 q] in v[q]
+    auto stage_b = [&](int jb_, int t_, const CPair<C> *tb) {
+        const C *sl = smem + t_ * V32_RS + jb_;
+#pragma unroll
+        for (int m = 0; m < 32; ++m) v[m] = sl[33 * m];
+        const CPair<C> *tp = tb + jb_;
+#pragma unroll
+        for (int p2 = 0; p2 < 16; ++p2) {
+            const CPair<C> w = ldg_pair_ordered(tp + p2 * 32);
+            if (p2 > 0) v[2 * p2] = cmul(v[2 * p2], w.a);
+            v[2 * p2 + 1] = cmul(v[2 * p2 + 1], w.b);
+        }
+        dft32(v);
+    };
+
+    // last stage output -> global: four-step twiddle W^{i k}, conj, mask, post-multiply
+    auto final_store = [&](int jb_, int t_) {
+        const unsigned i = i0 + t_;
+        C *dst = a.out + (long long)col * a.out_cs + (long long)i * a.out_is + (long long)jb_ * a.out_ks;
+        const long long kstep = (long long)32 * a.out_ks;
+        C c[4], s4 = mk<C>(1, 0);
+        if (OPT & FO_TWIDDLE) {
+            // W^{i (jb + 32 q)} = W^{i jb} * (W^{32 i})^q: four interleaved chains c[b] = W^{i jb} s^b, each stepped by s^4
+            const unsigned e = i * (unsigned)jb_;
+            c[0] = cmul(__ldg(a.twL + (e & a.tw_mask)), __ldg(a.twH + (e >> a.tw_shift)));
+            const C s1 = __ldg(a.twS + i);
+            const C s2 = cmul(s1, s1);
+            c[1] = cmul(c[0], s1);
+            c[2] = cmul(c[0], s2);
+            c[3] = cmul(c[1], s2);
+            s4 = cmul(s2, s2);
+        }
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            C val = v[q];
+            if (OPT & FO_TWIDDLE) {
+                val = cmul(val, c[q & 3]);
+                if (q + 4 < 32) c[q & 3] = cmul(c[q & 3], s4);
+            }
+            if (OPT & FO_OUT_CONJ) val = cconj(val);
+            const int k = jb_ + 32 * q;
+            bool ok = true;
+            const int mrow = k * a.out_lk + (int)i * a.out_li;
+            if (OPT & FO_OUT_MASK) ok = mrow < a.out_n;
+            if (OPT & FO_POST) {
+                if (ok) {
+                    const C pw = __ldg(a.post + mrow);
+                    val = (OPT & FO_POST_CONJ) ? cmulc(val, pw) : cmul(val, pw);
+                }
+            }
+            if (ok) {
+                if (STORE_T) dst[q * kstep] = val;
+                else dst[32 * q] = val;                                 // row-fastest: the output index is contiguous
+            }
+        }
+    };
+
+    if constexpr (!TWO) {
+        v32_sync<!LOAD_T && !STORE_T>();
+        v32_pos<STORE_T>(tid, jb, t);
+        stage_b(jb, t, tab);
+        final_store(jb, t);
+    } else {
+        // ---- middle pass of a convolution.  Inner stages are row-fastest: lane jb of warp t owns line t.
+        v32_sync<!LOAD_T>();
+        v32_pos<false>(tid, jb, t);
+        // spectrum values of this thread's outputs k = jb + 32 q, fetched four at a time, one batch ahead
+        const C *mp = a.mid + (long long)(i0 + t) * a.mid_is + jb;
+        C mv[2][4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mv[0][e] = ld_nc_ordered(mp + 32 * e);
+        stage_b(jb, t, tab);
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            if ((q & 3) == 0 && q + 4 < 32) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) mv[((q >> 2) + 1) & 1][e] = ld_nc_ordered(mp + 32 * (q + 4 + e));
+            }
+            const C w = mv[(q >> 2) & 1][q & 3];
+            v[q] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[q], w) : cmul(v[q], w));
+        }
+        // v[q] = position jb + 32 q: exactly the input of the next transform's first stage - no exchange
+        __syncwarp();                                                    // every lane has read its stage inputs
+        dft32(v);
+        {
+            C *sl = smem + t * V32_RS + jb * 33;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) sl[q] = v[q];
+        }
+        v32_sync<!STORE_T>();
+        v32_pos<STORE_T>(tid, jb, t);
+        stage_b(jb, t, tab + 512);            // second copy of the table: identical loads would be merged with the first
+        final_store(jb, t);                   // transform's and all sixteen pairs kept in registers across the pass
+    }
+}
+
+// ---- pass variants used by the engine (fft_engine.cu: run_v32); the intermediate is [k1][n2] (n2 contiguous)
+constexpr unsigned V32_A_F = FO_LOAD_T | FO_STORE_T | FO_TWIDDLE;                // first pass: strided in, strided out
+constexpr unsigned V32_A_FC = V32_A_F | FO_IN_CONJ;
+constexpr unsigned V32_A_M = V32_A_F | FO_IN_MASK;
+constexpr unsigned V32_A_MP = V32_A_M | FO_PRE;
+constexpr unsigned V32_A_MPC = V32_A_MP | FO_PRE_CONJ;
+constexpr unsigned V32_B_F = FO_STORE_T | FO_OUT_MASK;                           // second pass of a plain transform
+constexpr unsigned V32_B_FC = V32_B_F | FO_OUT_CONJ;
+constexpr unsigned V32_BM = FO_TWO_FFTS | FO_TWIDDLE;                            // middle pass: contiguous lines, in place
+constexpr unsigned V32_BMC = V32_BM | FO_MID_CONJ;
+constexpr unsigned V32_C_M = FO_LOAD_T | FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK; // last pass of a convolution
+constexpr unsigned V32_C_MP = V32_C_M | FO_POST;
+constexpr unsigned V32_C_MPC = V32_C_MP | FO_POST_CONJ;
+constexpr unsigned V32_K_A = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK;               // Kron: over i1 (stride), natural order out
+constexpr unsigned V32_K_AC = V32_K_A | FO_IN_CONJ;
+constexpr unsigned V32_K_B = FO_OUT_MASK;                                        // Kron: over i2 (contiguous)
+constexpr unsigned V32_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
+
+template <unsigned OPT> int launch_v32_variant(const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
+    static int attr_done = 0;
+    if (!attr_done) {
+        FMB_CUDA_OK(cudaFuncSetAttribute(v32_pass_kernel<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V32_SMEM));
+        attr_done = 1;
+    }
+    v32_pass_kernel<OPT><<<tiles, V32_NT, V32_SMEM, st>>>(a);
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+}
+
+}  // namespace fmb
