@@ -278,13 +278,15 @@ def run_ours(args):
     # (profiles/r1_traffic.json <- profiles/r1_launches_bench_circulant.csv); live numbers above are CUDA events only
     traffic = None
     kernels = {}
+    dominant = None
     try:
         with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
             tj = json.load(f)
         if cols == COLS:
             traffic = tj['dram_bytes_per_step']
         kernels = {k: {'share_of_step_time': v['share_of_step_time'], 'avg_us_under_ncu': v['avg_us']}
-                   for k, v in tj['kernels'].items()}
+                   for k, v in tj['kernels'].items() if v['share_of_step_time'] > 0.01}
+        dominant = tj.get('dominant_kernel')
     except Exception:
         pass
     del y
@@ -366,8 +368,12 @@ def run_ours(args):
                          'traffic': traffic, 'peak_source': peak_src,
                          'algorithmic_bytes_per_step': alg_bytes,
                          'note': ('operator level: algorithmic bytes of one step (2 x 8 B x N per column, SURVEY 8d) / CUDA-event '
-                                  'time of the step; one step = %d launches (3 passes per slab of %d columns); traffic = DRAM '
-                                  'bytes of the same launches from the committed ncu launch list') % (launches // steps, int(info.slab_cols)),
+                                  'time of the step on the caller stream; one step = %d launches (3 passes per slab of %d columns, '
+                                  'slabs issued round-robin on internal streams so a per-kernel event time does not exist); '
+                                  'kernels = each pass kernel\'s share of the step and traffic = DRAM bytes per step, both from '
+                                  'the committed ncu launch list of this command (profiles/r1_traffic.json)')
+                                 % (launches // steps, int(info.slab_cols)),
+                         'dominant_kernel': dominant,
                          'launches_per_step': launches // steps,
                          'kernels': kernels},
             'cpu_baseline': cpu,

@@ -79,7 +79,11 @@ struct EnginePlan : PlanBase {
         memset(o, 0, sizeof(*o));
         o->kind = kind; o->num_rows = num_rows; o->num_cols = num_cols;
         o->inner_size = eng.L; o->bluestein = bluestein_ref; o->passes_fwd = eng.passes();
-        o->slab_cols = eng.slab_cols(1 << 20, sizeof(float2));
+        {   // schedule of a large complex64 column batch (what bench.py reports)
+            int cols = 0, ns = 1;
+            eng.slab_plan(1 << 20, sizeof(float2), eng.shape.pow2, cols, ns);
+            o->slab_cols = cols;
+        }
         return FMB_OK;
     }
     int64_t workspace_bytes(int, int64_t M, int, int dt_out) const override { return eng.workspace_bytes(M, out_csize(dt_out)); }

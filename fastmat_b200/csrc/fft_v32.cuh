@@ -17,6 +17,9 @@
 
 namespace fmb {
 
+#ifndef V32_MINB
+#define V32_MINB 2
+#endif
 constexpr int V32_LOGT = 3, V32_T = 1 << V32_LOGT, V32_NT = 256;
 constexpr int V32_RS = 1058;                   // line stride: 1024 + one pad per 32, == 2 (mod 16) (see fft_fast.cuh)
 constexpr size_t V32_SMEM = (size_t)V32_T * V32_RS * sizeof(float2);
@@ -92,7 +95,7 @@ template <bool WARP> __device__ __forceinline__ void v32_sync() {
 }
 
 template <unsigned OPT>
-__global__ void __launch_bounds__(V32_NT, 2) v32_pass_kernel(const __grid_constant__ FastArgs<float2> a) {
+__global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid_constant__ FastArgs<float2> a) {
     typedef float2 C;
     extern __shared__ __align__(16) unsigned char fmb_v32_smem[];
     C *const smem = reinterpret_cast<C *>(fmb_v32_smem);
