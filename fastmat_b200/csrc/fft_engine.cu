@@ -648,7 +648,8 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
             a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
             a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
             a.tw = (const C *)d.twV[1].p;
-            if ((rc = launch_v32(bwd ? V32_B_FC : V32_B_F, a, tiles, st))) return rc;
+            const bool all_rows = rows_out == L;
+            if ((rc = launch_v32(bwd ? (all_rows ? V32_B_NC : V32_B_FC) : (all_rows ? V32_B_N : V32_B_F), a, tiles, st))) return rc;
         } else {
             {   // ---- pass B': in place on ws lines k1: FFT over n2, * spectrum[k1][k2], conj, FFT, * W^{k1 m2}
                 FastArgs<C> a = base;
@@ -665,7 +666,7 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
                 a.out_n = (int)rows_out; a.out_lk = R2; a.out_li = 1;
                 a.post = post_d;
                 a.tw = (const C *)d.twV[0].p;
-                unsigned opt = post_d ? (bwd ? V32_C_MPC : V32_C_MP) : V32_C_M;
+                unsigned opt = post_d ? (bwd ? V32_C_MPC : V32_C_MP) : (rows_out == L ? V32_C_N : V32_C_M);
                 if ((rc = launch_v32(opt, a, tiles, st))) return rc;
             }
         }

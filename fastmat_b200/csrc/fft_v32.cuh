@@ -113,14 +113,22 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
         const unsigned i = i0 + t;
         const C *src = a.in + (long long)col * a.in_cs + (long long)i * a.in_is + (long long)jb * a.in_fs;
         const long long fstep = (long long)32 * a.in_fs;
+        // zero padding: logical row f*in_lf + i*in_li < in_n  <=>  32 m < (number of valid f) - jb, one compare per value
+        int flim = 0;
+        if (OPT & FO_IN_MASK) {
+            const int room = a.in_n - (int)i * a.in_li;
+            flim = (room > 0 ? (room + a.in_lf - 1) / a.in_lf : 0) - jb;
+        }
 #pragma unroll
         for (int m = 0; m < 32; ++m) {
             const int f = jb + 32 * m;
             bool ok = true;
-            if (OPT & FO_IN_MASK) ok = (f * a.in_lf + (int)i * a.in_li) < a.in_n;
+            if (OPT & FO_IN_MASK) ok = 32 * m < flim;
             C val = mk<C>(0, 0);
+            // the address is formed outside the predicate so that a masked load is one predicated LDG, not a branch
+            const C *pl = LOAD_T ? src + m * fstep : src + 32 * m;      // row-fastest: the transform index is contiguous
             if (ok) {
-                val = LOAD_T ? src[m * fstep] : src[32 * m];          // row-fastest: the transform index is contiguous
+                val = *pl;
                 if (OPT & FO_IN_CONJ) val = cconj(val);
                 if (OPT & FO_PRE) {
                     const C w = __ldg(a.pre + (f * a.in_lf + (int)i * a.in_li));
@@ -170,6 +178,11 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
             c[3] = cmul(c[1], s2);
             s4 = cmul(s2, s2);
         }
+        int klim = 0;                                                    // truncation: k*out_lk + i*out_li < out_n
+        if (OPT & FO_OUT_MASK) {
+            const int room = a.out_n - (int)i * a.out_li;
+            klim = (room > 0 ? (room + a.out_lk - 1) / a.out_lk : 0) - jb_;
+        }
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             C val = v[q];
@@ -181,17 +194,15 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
             const int k = jb_ + 32 * q;
             bool ok = true;
             const int mrow = k * a.out_lk + (int)i * a.out_li;
-            if (OPT & FO_OUT_MASK) ok = mrow < a.out_n;
+            if (OPT & FO_OUT_MASK) ok = 32 * q < klim;
             if (OPT & FO_POST) {
                 if (ok) {
                     const C pw = __ldg(a.post + mrow);
                     val = (OPT & FO_POST_CONJ) ? cmulc(val, pw) : cmul(val, pw);
                 }
             }
-            if (ok) {
-                if (STORE_T) dst[q * kstep] = val;
-                else dst[32 * q] = val;                                 // row-fastest: the output index is contiguous
-            }
+            C *ps = STORE_T ? dst + q * kstep : dst + 32 * q;          // row-fastest: the output index is contiguous
+            if (ok) *ps = val;
         }
     };
 
@@ -242,9 +253,12 @@ constexpr unsigned V32_A_MP = V32_A_M | FO_PRE;
 constexpr unsigned V32_A_MPC = V32_A_MP | FO_PRE_CONJ;
 constexpr unsigned V32_B_F = FO_STORE_T | FO_OUT_MASK;                           // second pass of a plain transform
 constexpr unsigned V32_B_FC = V32_B_F | FO_OUT_CONJ;
+constexpr unsigned V32_B_N = FO_STORE_T;                                         // ... all rows kept: no store mask
+constexpr unsigned V32_B_NC = V32_B_N | FO_OUT_CONJ;
 constexpr unsigned V32_BM = FO_TWO_FFTS | FO_TWIDDLE;                            // middle pass: contiguous lines, in place
 constexpr unsigned V32_BMC = V32_BM | FO_MID_CONJ;
 constexpr unsigned V32_C_M = FO_LOAD_T | FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK; // last pass of a convolution
+constexpr unsigned V32_C_N = FO_LOAD_T | FO_STORE_T | FO_OUT_CONJ;               // ... all rows kept: no store mask
 constexpr unsigned V32_C_MP = V32_C_M | FO_POST;
 constexpr unsigned V32_C_MPC = V32_C_MP | FO_POST_CONJ;
 constexpr unsigned V32_K_A = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK;               // Kron: over i1 (stride), natural order out

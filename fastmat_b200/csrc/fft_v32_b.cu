@@ -10,6 +10,8 @@ int launch_v32_b(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaSt
         case V32_K_AC: return launch_v32_variant<V32_K_AC>(a, tiles, st);
         case V32_K_B: return launch_v32_variant<V32_K_B>(a, tiles, st);
         case V32_K_BC: return launch_v32_variant<V32_K_BC>(a, tiles, st);
+        case V32_B_N: return launch_v32_variant<V32_B_N>(a, tiles, st);
+        case V32_B_NC: return launch_v32_variant<V32_B_NC>(a, tiles, st);
         default: return FMB_ERR_NOTIMPL;
     }
 }
