@@ -83,6 +83,20 @@ __device__ __forceinline__ CPair<float2> ldg_pair_ordered(const CPair<float2> *p
     return r;
 }
 
+// dft32 whose odd inputs are prepared by `prep_odd()` only after the even half has been transformed: the middle pass
+// uses it to overlap the latency of the second half of its spectrum loads with sixteen-point butterflies
+template <typename C, typename PrepOdd> __device__ __forceinline__ void dft32_late_odd(C (&v)[32], PrepOdd prep_odd) {
+    C e[16], o[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) e[r] = v[2 * r];
+    dft16(e);
+    prep_odd();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) o[r] = v[2 * r + 1];
+    dft16(o);
+    dft32_combine<C, 0>(v, e, o);
+}
+
 template <bool ORDER_T> __device__ __forceinline__ void v32_pos(int tid, int &jb, int &t) {
     if (ORDER_T) { t = tid & (V32_T - 1); jb = tid >> V32_LOGT; }
     else { jb = tid & 31; t = tid >> 5; }
@@ -215,24 +229,26 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
         // ---- middle pass of a convolution.  Inner stages are row-fastest: lane jb of warp t owns line t.
         v32_sync<!LOAD_T>();
         v32_pos<false>(tid, jb, t);
-        // spectrum values of this thread's outputs k = jb + 32 q, fetched four at a time, one batch ahead
+        // Spectrum values of this thread's outputs k = jb + 32 q (one L2 round trip each): those of the even q are
+        // requested now - the registers of v are free between the exchange store and load - and arrive during the second
+        // stage; those of the odd q are requested once the even ones are consumed and arrive during the even half of the
+        // next transform's first butterfly.  (Fetched a few at a time they cost eight exposed round trips per tile.)
         const C *mp = a.mid + (long long)(i0 + t) * a.mid_is + jb;
-        C mv[2][4];
+        C mh[16];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) mv[0][e] = ld_nc_ordered(mp + 32 * e);
+        for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r));
         stage_b(jb, t, tab);
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            if ((q & 3) == 0 && q + 4 < 32) {
+        for (int r = 0; r < 16; ++r) v[2 * r] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r], mh[r]) : cmul(v[2 * r], mh[r]));
 #pragma unroll
-                for (int e = 0; e < 4; ++e) mv[((q >> 2) + 1) & 1][e] = ld_nc_ordered(mp + 32 * (q + 4 + e));
-            }
-            const C w = mv[(q >> 2) & 1][q & 3];
-            v[q] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[q], w) : cmul(v[q], w));
-        }
+        for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r + 1));
         // v[q] = position jb + 32 q: exactly the input of the next transform's first stage - no exchange
         __syncwarp();                                                    // every lane has read its stage inputs
-        dft32(v);
+        dft32_late_odd(v, [&]() {
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+                v[2 * r + 1] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r + 1], mh[r]) : cmul(v[2 * r + 1], mh[r]));
+        });
         {
             C *sl = smem + t * V32_RS + jb * 33;
 #pragma unroll
