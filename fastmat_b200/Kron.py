@@ -73,6 +73,25 @@ class Kron(Matrix):
             return plan_apply(self._plan, BACKWARD, fft_in_prepare(x, ft_out), self._numRows, ft_out)
         return self._chain(x, True)
 
+    # analytic overrides: fastmat/Kron.pyx:155-183
+    def _getLargestSingularValue(self):
+        v = 1.0
+        for f in self._content:
+            v *= float(f.largestSingularValue)
+        return v
+
+    def _getColNorms(self):
+        n = self._content[0].colNorms
+        for f in self._content[1:]:
+            n = torch.kron(n, f.colNorms)
+        return n
+
+    def _getRowNorms(self):
+        n = self._content[0].rowNorms
+        for f in self._content[1:]:
+            n = torch.kron(n, f.rowNorms)
+        return n
+
     def _reference(self):
         """fastmat/Kron.pyx:344-353: np.kron of the factor references."""
         arr = None

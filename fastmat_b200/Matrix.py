@@ -451,7 +451,8 @@ class Matrix(object):
         dev = self._default_device()
         out = torch.empty(self.numCols, dtype=torch.float64, device=dev)
         chunk = max(1, min(self.numCols, (1 << 24) // max(1, self.numRows)))
-        tt = _t.getTorchType(_t.promoteTypes(self._fusedType, _t.TYPE_FLOAT32))
+        # in double: the norms feed step sizes / normalisations of the solvers (the reference's FFT classes are complex128)
+        tt = _t.getTorchType(_t.promoteTypes(self._fusedType, _t.TYPE_FLOAT64))
         for c0 in range(0, self.numCols, chunk):
             c1 = min(self.numCols, c0 + chunk)
             sel = torch.zeros((self.numCols, c1 - c0), dtype=tt, device=dev)

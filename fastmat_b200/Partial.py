@@ -95,6 +95,19 @@ class Partial(Matrix):
             y = plan_apply(self._colPlan, FORWARD, y, self._numCols, _t.getFusedType(y.dtype))
         return y
 
+    # norms of a pure row / column selection follow from the nested matrix (fastmat/Partial.pyx:234-250)
+    def _getColNorms(self):
+        if self._rowSelection is not None:
+            return super(Partial, self)._getColNorms()
+        n = self._content[0].colNorms
+        return n if self._colSelection is None else n[torch.from_numpy(self._colSelection).to(n.device)]
+
+    def _getRowNorms(self):
+        if self._colSelection is not None:
+            return super(Partial, self)._getRowNorms()
+        n = self._content[0].rowNorms
+        return n if self._rowSelection is None else n[torch.from_numpy(self._rowSelection).to(n.device)]
+
     def _reference(self):
         full = self._content[0].reference()
         if self._rowSelection is not None:

@@ -104,6 +104,33 @@ class Product(Matrix):
             r = f.backward(r)
         return r
 
+    # Exact shortcuts the generic unit-vector sweep (fastmat/Matrix.pyx:1048-1088) does not need: a trailing Diag scales
+    # the columns, a leading Diag the rows, a scalar both.  Needed to make OMP's colNormalized affordable for the
+    # compressed-sensing operator Product(Partial(Fourier), Diag) with 2^18 columns.
+    def _getColNorms(self):
+        from .Diag import Diag
+        c = self._content
+        if len(c) >= 1 and isinstance(c[-1], Diag):
+            rest = c[0].colNorms if len(c) == 2 else (Product(*c[:-1]).colNorms if len(c) > 2 else None)
+            d = c[-1].colNorms
+            n = d if rest is None else rest * d
+            return n * abs(self._scalar)
+        if len(c) == 1:
+            return c[0].colNorms * abs(self._scalar)
+        return super(Product, self)._getColNorms()
+
+    def _getRowNorms(self):
+        from .Diag import Diag
+        c = self._content
+        if len(c) >= 1 and isinstance(c[0], Diag):
+            rest = c[1].rowNorms if len(c) == 2 else (Product(*c[1:]).rowNorms if len(c) > 2 else None)
+            d = c[0].rowNorms
+            n = d if rest is None else rest * d
+            return n * abs(self._scalar)
+        if len(c) == 1:
+            return c[0].rowNorms * abs(self._scalar)
+        return super(Product, self)._getRowNorms()
+
     def _reference(self):
         arr = None
         for f in self._content:

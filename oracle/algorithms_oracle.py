@@ -89,6 +89,39 @@ def omp(A, b, numMaxSteps):
     return x
 
 
+def stela(A, b, numLambda=0.1, numMaxSteps=100, numMaxError=1e-6):
+    """fastmat/algorithms/STELA.py:128-262."""
+    b2 = b.reshape(-1, 1) if b.ndim == 1 else b
+    dt = np.promote_types(np.float64, b2.dtype)
+    gamma = np.zeros(b2.shape[1], dtype=dt)
+    x = np.zeros((A.shape[1], b2.shape[1]), dtype=dt)
+    res = (-b2).astype(dt)
+    bx = np.zeros_like(x, dtype=dt)
+    abxx = np.zeros_like(b2, dtype=dt)
+    AH = A.conj().T
+    z = AH @ res
+    d = (1.0 / np.linalg.norm(A, axis=0) ** 2).reshape((-1, 1))
+    for _ in range(numMaxSteps):
+        grad = d * x - z
+        diff = np.maximum(np.minimum(z.real - x.real, +numLambda), -numLambda)
+        if dt == complex:
+            diff = diff + 1j * np.maximum(np.minimum(z.imag - x.imag, +numLambda), -numLambda)
+        stop = np.linalg.norm(z - diff, axis=0)
+        act = stop > numMaxError
+        if np.sum(act) == 0:
+            return x
+        bx[:, act] = soft_threshold(grad[:, act], numLambda) / d
+        abxx[:, act] = A @ (bx[:, act] - x[:, act])
+        gamma[act] = np.maximum(np.minimum(
+            -(np.real(np.sum(np.multiply(np.conj(res[:, act]), abxx[:, act]), axis=0))
+              + numLambda * (np.sum(np.abs(bx[:, act]) - np.abs(x[:, act]), axis=0)))
+            / np.sum(np.abs(abxx[:, act]) ** 2, axis=0), 1), 0)
+        x[:, act] += (bx[:, act] - x[:, act]).dot(np.diag(gamma[act]))
+        res[:, act] += gamma[act] * abxx[:, act]
+        z[:, act] = AH @ res[:, act]
+    return x
+
+
 # ---- the compressed-sensing operator of BASELINE config 5, as a dense matrix
 def cs_matrix_fourier(n, rows, d):
     """dense Product(Partial(Fourier(n), rows=rows), Diag(d)) (fastmat/Fourier.pyx:241-246, Partial.pyx:296-307, Diag.pyx:169-176)."""

@@ -38,6 +38,8 @@ def run(tag, A, x, lam, steps, k):
     arrs[tag + '_ista'] = fma.ISTA(A, numLambda=lam, numMaxSteps=steps).process(b)
     arrs[tag + '_fista'] = fma.FISTA(A, numLambda=lam, numMaxSteps=steps).process(b)
     arrs[tag + '_omp'] = fma.OMP(A, numMaxSteps=k).process(b)
+    # STELA amplifies rounding differences step by step (its line-search steps are tiny on these problems): 8 steps
+    arrs[tag + '_stela'] = fma.STELA(A, numLambda=lam, numMaxSteps=8).process(b)
     arrs[tag + '_params'] = np.asarray([lam, steps, k], dtype=float)
 
 

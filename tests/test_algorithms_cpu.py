@@ -58,3 +58,11 @@ def test_soft_threshold_definition():
     assert np.allclose(y, [-2.0, 0.0, 0.0, 0.0, 1.0])
     z = ao.soft_threshold(np.array([3 + 4j]), 1.0)                  # shrinks the modulus, keeps the phase
     assert np.allclose(z, (3 + 4j) * 4.0 / 5.0)
+
+
+@pytest.mark.parametrize('tag', ['cs', 'had'])
+def test_oracle_stela_matches_reference(tag):
+    A, b, lam, _, _ = problem(tag)
+    got = ao.stela(A, b, numLambda=lam, numMaxSteps=8)
+    ref = GA[tag + '_stela']
+    assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max()

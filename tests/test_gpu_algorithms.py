@@ -141,3 +141,36 @@ def test_config5_compressed_sensing_recovery(fm):
     r0 = float(torch.linalg.vector_norm(b))
     r1 = float(torch.linalg.vector_norm(A.forward(res) - b))
     assert r1 < 0.2 * r0
+
+
+def test_norm_and_singular_value_shortcuts(fm):
+    """colNorms / rowNorms / largestSingularValue overrides (fastmat/Partial.pyx:234-250, Kron.pyx:155-183, plus the
+    exact Diag-factor shortcut of Product) against the dense reference matrix."""
+    rng = np.random.default_rng(11)
+    d = (rng.standard_normal(64) + 1j * rng.standard_normal(64)).astype(np.complex128)
+    rows = np.sort(rng.choice(64, 20, replace=False))
+    cols = np.sort(rng.choice(64, 33, replace=False))
+    mats = [fm.Partial(fm.Fourier(64), cols=cols), fm.Partial(fm.Hadamard(6), rows=rows),
+            fm.Partial(fm.Fourier(64), rows=rows, cols=cols), fm.Kron(fm.Fourier(8), fm.Hadamard(3)),
+            fm.Product(fm.Partial(fm.Fourier(64), rows=rows), fm.Diag(d)), fm.Product(fm.Diag(d), fm.Fourier(64)),
+            fm.Product(fm.Diag(d), fm.Partial(fm.Fourier(64), cols=cols), 2.5)]
+    for M in mats:
+        ref = M.reference().to(torch.complex128)
+        assert ref.shape == (M.numRows, M.numCols)
+        cn = torch.linalg.vector_norm(ref, dim=0)
+        rn = torch.linalg.vector_norm(ref, dim=1)
+        assert float((M.colNorms.to(torch.float64) - cn).abs().max()) <= 1e-9 * float(cn.max()), repr(M)
+        assert float((M.rowNorms.to(torch.float64) - rn).abs().max()) <= 1e-9 * float(rn.max()), repr(M)
+        s = float(torch.linalg.matrix_norm(ref, ord=2))
+        assert abs(M.largestSingularValue - s) <= 1e-8 * s, repr(M)
+
+
+@pytest.mark.parametrize('tag', ['cs', 'had'])
+def test_stela_matches_reference(fm, tag):
+    A = build(fm, tag, np.complex128)
+    lam = float(GA[tag + '_params'][0])
+    b = GA[tag + '_b']
+    got = fm.algorithms.STELA(A, numLambda=lam, numMaxSteps=8).process(colmajor(b)).cpu().numpy()
+    ref = GA[tag + '_stela']
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-7 * np.abs(ref).max()
