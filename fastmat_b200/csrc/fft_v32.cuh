@@ -142,7 +142,11 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
             // the address is formed outside the predicate so that a masked load is one predicated LDG, not a branch
             const C *pl = LOAD_T ? src + m * fstep : src + 32 * m;      // row-fastest: the transform index is contiguous
             if (ok) {
+#ifdef V32_DEBUG_NOLOAD                                                 /* timing experiment only: how much do the input loads cost? */
+                val = mk<C>((float)(jb + m) * 1e-3f, (float)(t + (int)(reinterpret_cast<size_t>(pl) & 1)));
+#else
                 val = *pl;
+#endif
                 if (OPT & FO_IN_CONJ) val = cconj(val);
                 if (OPT & FO_PRE) {
                     const C w = __ldg(a.pre + (f * a.in_lf + (int)i * a.in_li));
@@ -168,7 +172,11 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
         const CPair<C> *tp = tb + jb_;
 #pragma unroll
         for (int p2 = 0; p2 < 16; ++p2) {
+#ifdef V32_DEBUG_NOTW                                                   /* timing experiment only */
+            CPair<C> w; w.a = mk<C>(0.5f + (float)p2, 0.25f); w.b = mk<C>(0.75f, (float)jb_);
+#else
             const CPair<C> w = ldg_pair_ordered(tp + p2 * 32);
+#endif
             if (p2 > 0) v[2 * p2] = cmul(v[2 * p2], w.a);
             v[2 * p2 + 1] = cmul(v[2 * p2 + 1], w.b);
         }
@@ -216,7 +224,11 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
                 }
             }
             C *ps = STORE_T ? dst + q * kstep : dst + 32 * q;          // row-fastest: the output index is contiguous
+#ifdef V32_DEBUG_NOSTORE                                                /* timing experiment only */
+            if (ok && val.x == 1.2345e30f) *ps = val;
+#else
             if (ok) *ps = val;
+#endif
         }
     };
 

@@ -1,5 +1,4 @@
 #!/bin/bash
-for cfg in "3 16" "4 16"; do
-  set -- $cfg
-  FMB_PIPE_STREAMS=$1 FMB_PIPE_MB=$2 python tools/sweep.py 256 2>&1 | tail -1 | sed -e 's/chk [^|]*|/|/'
+for lib in "" build/alt/lib_noload.so build/alt/lib_NOSTORE.so build/alt/lib_NOTW.so build/alt/lib_NOLDST.so build/alt/lib_NOALL.so; do
+  echo "lib=$lib"; FMB_LIB_PATH=${lib:+$PWD/$lib} python tools/sweep.py 256 2>&1 | tail -1 | sed -e 's/chk [^|]*|/|/'
 done
