@@ -121,6 +121,7 @@ struct PipeScope {
     std::unique_lock<std::mutex> lock;
     int ns = 1;
     cudaStream_t caller = nullptr;
+    void *pool_ = nullptr;              // the device's stream pool (fft_engine.cu)
     int begin(int ns_, cudaStream_t st);
     cudaStream_t stream(int64_t k) const;
     int end();

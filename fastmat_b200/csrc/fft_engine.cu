@@ -285,48 +285,46 @@ int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
 // interleave
 struct StreamPool {
     std::mutex mu;
-    int device = -1;
     cudaStream_t s[FMB_MAX_PIPE] = {};
     cudaEvent_t fork = nullptr, join[FMB_MAX_PIPE] = {};
     bool ready = false;
-    int ensure() {
-        int dev = 0;
-        FMB_CUDA_OK(cudaGetDevice(&dev));
-        if (ready && dev == device) return FMB_OK;
-        if (ready) {
-            for (int i = 0; i < FMB_MAX_PIPE; ++i) { cudaStreamDestroy(s[i]); cudaEventDestroy(join[i]); }
-            cudaEventDestroy(fork);
-            ready = false;
-        }
+    int ensure() {                       // called with mu held, on the pool of the current device
+        if (ready) return FMB_OK;
         for (int i = 0; i < FMB_MAX_PIPE; ++i) {
             FMB_CUDA_OK(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
             FMB_CUDA_OK(cudaEventCreateWithFlags(&join[i], cudaEventDisableTiming));
         }
         FMB_CUDA_OK(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-        device = dev;
         ready = true;
         return FMB_OK;
     }
 };
-static StreamPool g_pool;
+constexpr int FMB_MAX_DEVICES = 64;
+static StreamPool g_pools[FMB_MAX_DEVICES];     // one per device ordinal (streams belong to a device)
 
 int PipeScope::begin(int ns_, cudaStream_t st) {
     caller = st;
     ns = std::max(1, std::min(ns_, (int)FMB_MAX_PIPE));
     if (ns == 1) return FMB_OK;
-    lock = std::unique_lock<std::mutex>(g_pool.mu);
-    int rc = g_pool.ensure();
+    int dev = 0;
+    FMB_CUDA_OK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= FMB_MAX_DEVICES) { ns = 1; return FMB_OK; }
+    StreamPool &pool = g_pools[dev];
+    pool_ = &pool;
+    lock = std::unique_lock<std::mutex>(pool.mu);
+    int rc = pool.ensure();
     if (rc) return rc;
-    FMB_CUDA_OK(cudaEventRecord(g_pool.fork, st));
-    for (int i = 0; i < ns; ++i) FMB_CUDA_OK(cudaStreamWaitEvent(g_pool.s[i], g_pool.fork, 0));
+    FMB_CUDA_OK(cudaEventRecord(pool.fork, st));
+    for (int i = 0; i < ns; ++i) FMB_CUDA_OK(cudaStreamWaitEvent(pool.s[i], pool.fork, 0));
     return FMB_OK;
 }
-cudaStream_t PipeScope::stream(int64_t k) const { return ns > 1 ? g_pool.s[k % ns] : caller; }
+cudaStream_t PipeScope::stream(int64_t k) const { return ns > 1 ? static_cast<StreamPool *>(pool_)->s[k % ns] : caller; }
 int PipeScope::end() {
     if (ns == 1) return FMB_OK;
+    StreamPool &pool = *static_cast<StreamPool *>(pool_);
     for (int i = 0; i < ns; ++i) {
-        FMB_CUDA_OK(cudaEventRecord(g_pool.join[i], g_pool.s[i]));
-        FMB_CUDA_OK(cudaStreamWaitEvent(caller, g_pool.join[i], 0));
+        FMB_CUDA_OK(cudaEventRecord(pool.join[i], pool.s[i]));
+        FMB_CUDA_OK(cudaStreamWaitEvent(caller, pool.join[i], 0));
     }
     lock.unlock();
     return FMB_OK;
