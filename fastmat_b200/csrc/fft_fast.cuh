@@ -79,6 +79,17 @@ enum : unsigned {
 };
 
 template <typename C> __device__ __forceinline__ C ld_cg(const C *p) { return __ldcg(p); }
+// streaming load of a pass input: each element is used once per launch and should not displace the twiddle tables from L1
+__device__ __forceinline__ float2 ld_stream(const float2 *p) {
+    float2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ double2 ld_stream(const double2 *p) {
+    double2 r;
+    asm volatile("ld.global.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+    return r;
+}
 
 // read-only load whose position in the instruction stream is kept relative to the other loads of its kind (volatile,
 // but no memory clobber): the spectrum loads of the middle pass are software-pipelined by hand, four values ahead of
@@ -199,7 +210,7 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
             C val = mk<C>(0, 0);
             if (ok) {
                 const C *p = src + (long long)(ROWS * m) * a.in_fs;
-                val = (OPT & FO_IN_CG) ? ld_cg(p) : *p;
+                val = (OPT & FO_IN_CG) ? ld_cg(p) : ld_stream(p);
                 if (OPT & FO_IN_CONJ) val = cconj(val);
                 if (OPT & FO_PRE) {
                     const C w = __ldg(a.pre + (f * a.in_lf + (int)i * a.in_li));

@@ -102,8 +102,6 @@ template <typename C, typename PrepOdd> __device__ __forceinline__ void dft32_la
     dft32_combine<C, 0>(v, e, o);
 }
 
-// streaming load of the pass input: every element is used once per launch, so it should not displace the twiddle tables
-// from L1
 __device__ __forceinline__ float2 ld_nc_stream(const float2 *p) {
     float2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
@@ -112,12 +110,6 @@ __device__ __forceinline__ float2 ld_nc_stream(const float2 *p) {
 __device__ __forceinline__ void st_stream(float2 *p, float2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
-__device__ __forceinline__ float2 ld_stream(const float2 *p) {
-    float2 r;
-    asm volatile("ld.global.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
-
 template <bool ORDER_T> __device__ __forceinline__ void v32_pos(int tid, int &jb, int &t) {
     if (ORDER_T) { t = tid & (V32_T - 1); jb = tid >> V32_LOGT; }
     else { jb = tid & 31; t = tid >> 5; }
