@@ -348,7 +348,7 @@ def run_ours(args):
         rec('fourier_forward_2^16_c128_64cols', timed(lambda: F16.forward(x16), 10, 3), 64, 32.0 * (1 << 16))
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and not args.no_cpu and not distributed:          # reported at N = 1 only
         cpu = cpu_baseline_single(cols=args.cpu_cols, reps=2)
 
     if rank == 0:
