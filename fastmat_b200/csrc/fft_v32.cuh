@@ -20,11 +20,6 @@ namespace fmb {
 #ifndef V32_MINB
 #define V32_MINB 2
 #endif
-#ifdef V32_STREAM_MID
-#define V32_MID_LOAD ld_nc_stream
-#else
-#define V32_MID_LOAD ld_nc_ordered
-#endif
 constexpr int V32_LOGT = 3, V32_T = 1 << V32_LOGT, V32_NT = 256;
 constexpr int V32_RS = 1058;                   // line stride: 1024 + one pad per 32, == 2 (mod 16) (see fft_fast.cuh)
 constexpr size_t V32_SMEM = (size_t)V32_T * V32_RS * sizeof(float2);
@@ -102,14 +97,6 @@ template <typename C, typename PrepOdd> __device__ __forceinline__ void dft32_la
     dft32_combine<C, 0>(v, e, o);
 }
 
-__device__ __forceinline__ float2 ld_nc_stream(const float2 *p) {
-    float2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ void st_stream(float2 *p, float2 v) {
-    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
 template <bool ORDER_T> __device__ __forceinline__ void v32_pos(int tid, int &jb, int &t) {
     if (ORDER_T) { t = tid & (V32_T - 1); jb = tid >> V32_LOGT; }
     else { jb = tid & 31; t = tid >> 5; }
@@ -241,8 +228,6 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
             C *ps = STORE_T ? dst + q * kstep : dst + 32 * q;          // row-fastest: the output index is contiguous
 #ifdef V32_DEBUG_NOSTORE                                                /* timing experiment only */
             if (ok && val.x == 1.2345e30f) *ps = val;
-#elif defined(V32_STREAM_STORES)
-            if (ok) st_stream(ps, val);
 #else
             if (ok) *ps = val;
 #endif
@@ -265,12 +250,12 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
         const C *mp = a.mid + (long long)(i0 + t) * a.mid_is + jb;
         C mh[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) mh[r] = V32_MID_LOAD(mp + 32 * (2 * r));
+        for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r));
         stage_b(jb, t, tab);
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[2 * r] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r], mh[r]) : cmul(v[2 * r], mh[r]));
 #pragma unroll
-        for (int r = 0; r < 16; ++r) mh[r] = V32_MID_LOAD(mp + 32 * (2 * r + 1));
+        for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r + 1));
         // v[q] = position jb + 32 q: exactly the input of the next transform's first stage - no exchange
         __syncwarp();                                                    // every lane has read its stage inputs
         dft32_late_odd(v, [&]() {
