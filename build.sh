@@ -14,7 +14,7 @@ if [ "${EMUL:-0}" = "1" ]; then
 else
   mkdir -p fastmat_b200/lib build
   OBJS=""
-  for f in capi fft_engine fft_k_f32_pow2 fft_k_f32_gen fft_k_f64_pow2 fft_k_f64_gen fft_fast_f32_L8 fft_fast_f32_L9 fft_fast_f32_L10 fft_fast_f32_L11 fft_fast_f32_L12 fft_v32_a fft_v32_b fft_v32_m fft_v32_c fft_fast_f64_L8 fft_fast_f64_L9 fft_fast_f64_L10 fft_fast_f64_L11 fft_fused_f32_8_8 fft_fused_f32_8_9 fft_fused_f32_9_9 fft_fused_f32_9_10 fft_fused_f32_10_10 fft_fused_f32_10_11 fft_fused_f32_11_11 fft_fused_f64_8_8 fwht elementwise; do
+  for f in capi fft_engine fft_k_f32_pow2 fft_k_f32_gen fft_k_f64_pow2 fft_k_f64_gen fft_fast_f32_L8 fft_fast_f32_L9 fft_fast_f32_L10 fft_fast_f32_L11 fft_fast_f32_L12 fft_v32_a fft_v32_b fft_v32_m fft_v32_c fft_v32p_f fft_v32p_c0 fft_v32p_c1 fft_fast_f64_L8 fft_fast_f64_L9 fft_fast_f64_L10 fft_fast_f64_L11 fft_fused_f32_8_8 fft_fused_f32_8_9 fft_fused_f32_9_9 fft_fused_f32_9_10 fft_fused_f32_10_10 fft_fused_f32_10_11 fft_fused_f32_11_11 fft_fused_f64_8_8 fwht elementwise; do
     $NVCC $COMMON ${PTXAS_V:+-Xptxas -v} -gencode arch=compute_100a,code=sm_100a -c $SRC/$f.cu -o build/$f.o &
     OBJS="$OBJS build/$f.o"
   done

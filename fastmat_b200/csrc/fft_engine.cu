@@ -7,6 +7,7 @@
 #include "fft_fast.cuh"
 #include "fft_fused.cuh"
 #include "fft_v32.cuh"
+#include "fft_v32p.cuh"
 #include "fft_pass.cuh"
 
 namespace fmb {
@@ -275,6 +276,7 @@ int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
         slab_plan(M, csize, true, cols, ns);
         int64_t w = std::max(generic, (int64_t)cols * ns * L * (int64_t)csize);
         if (kron_a == 0) w = std::max(w, fused_workspace_bytes(M, csize));
+        if (kron_a == 0 && csize == sizeof(float2)) w = std::max(w, v32p_workspace_bytes(M));
         return w;
     }
     return generic;
@@ -674,6 +676,168 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
 #endif
 }
 
+
+// ------------------------------------------------------------------------------------------- V32P path (fft_v32p.cuh)
+int launch_v32p_f(int variant, const V32PArgs &g, const CUtensorMap &mx, const CUtensorMap &mr, cudaStream_t st);
+int launch_v32p_c0(int variant, const V32PArgs &g, const CUtensorMap &mx, const CUtensorMap &mr, cudaStream_t st);
+int launch_v32p_c1(int variant, const V32PArgs &g, const CUtensorMap &mx, const CUtensorMap &mr, cudaStream_t st);
+
+struct V32PGeom { int slab_cols, delay, nslot, npass, mix; int64_t nslabs, counter_bytes, ring_bytes; unsigned tiles, items_per_step; };
+static V32PGeom v32p_geom(int64_t M, int64_t L, bool two) {
+    static const long slab_env = env_long("FMB_V32P_SLAB", 2), delay_env = env_long("FMB_V32P_DELAY", 0),
+                      mix_env = env_long("FMB_V32P_MIX", 1);
+    V32PGeom f;
+    f.npass = two ? 3 : 2;
+    f.mix = mix_env ? 1 : 0;
+    f.slab_cols = (int)std::max<long>(1, std::min<long>(slab_env, 64));
+    f.tiles = (unsigned)f.slab_cols * 128u;
+    f.items_per_step = (unsigned)f.npass * f.tiles;
+    // Correctness does not depend on D (fft_v32p.cuh); speed does: a tile is requested up to three items per CTA ahead of
+    // its arithmetic and completions are published a little late, so producers should be >= AHEAD * G items back.
+    //   blocked order:     distance = D S + 1;   interleaved order:  distance = (D - 1) S + npass + 1     (S = items per step)
+    static const long ahead_env = env_long("FMB_V32P_AHEAD", 5);
+    const int64_t G = device_props().sm_count, S = f.items_per_step, need = std::max<long>(1, ahead_env) * G;
+    int dmin = 1;
+    while ((f.mix ? (int64_t)(dmin - 1) * S + f.npass + 1 : (int64_t)dmin * S + 1) < need) ++dmin;
+    f.delay = (int)std::max<long>(dmin, delay_env);
+    // the slot of slab s is reused by slab s + nslot, whose pass A waits for the last pass of slab s: same slack again
+    f.nslot = (f.npass - 1) * f.delay + 1 + (int)((need + S - 1) / S);
+    f.nslabs = (M + f.slab_cols - 1) / f.slab_cols;
+    f.counter_bytes = ((int64_t)4 * 3 * f.nslabs + 1023) / 1024 * 1024;
+    f.ring_bytes = (int64_t)f.nslot * f.slab_cols * L * (int64_t)sizeof(float2);
+    return f;
+}
+
+int64_t ConvEngine::v32p_workspace_bytes(int64_t M) const {
+    if (!v32_ok(sizeof(float2))) return 0;
+    const V32PGeom f = v32p_geom(M, L, two_ffts);
+    return f.counter_bytes + f.ring_bytes;
+}
+
+typedef CUresult (*fmb_encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                        const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static fmb_encode_tiled_fn encode_tiled_fn() {
+#ifdef FMB_EMULATE
+    return nullptr;
+#else
+    static fmb_encode_tiled_fn fn = []() -> fmb_encode_tiled_fn {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (fmb_encode_tiled_fn)p;
+    }();
+    return fn;
+#endif
+}
+
+// tensor of complex64 (as 8-byte words) [cols][rows / 1024][1024]; a request is a box of 8 words x 256 rows x 1 column
+static int v32p_tensor_map(CUtensorMap *map, const void *base, int64_t rows, int64_t col_stride, int64_t cols) {
+    static const long promo = env_long("FMB_V32P_PROMO", 0);
+    fmb_encode_tiled_fn enc = encode_tiled_fn();
+    if (!enc) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return FMB_ERR_CUDA; }
+    const cuuint64_t dims[3] = {1024, (cuuint64_t)(rows / 1024), (cuuint64_t)cols};
+    const cuuint64_t strides[2] = {8192, (cuuint64_t)col_stride * sizeof(float2)};
+    const cuuint32_t box[3] = {8, 256, 1}, estr[3] = {1, 1, 1};
+    const CUtensorMapL2promotion pr = promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                    : promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE;
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, const_cast<void *>(base), dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return FMB_ERR_CUDA; }
+    return FMB_OK;
+}
+
+bool ConvEngine::v32p_ok(int direction, const void *x, int64_t xcs, const void *y, int64_t ycs) const {
+#ifdef FMB_EMULATE
+    return false;
+#else
+    static const long on = env_long("FMB_V32P", 1);
+    if (!on || kron_a > 0 || !pre.empty() || !post.empty()) return false;
+    const int64_t rows_in = direction == FMB_BACKWARD ? n_out : n_in, rows_out = direction == FMB_BACKWARD ? n_in : n_out;
+    if (rows_in <= 0 || rows_in % 1024 != 0) return false;              // zero padding = out-of-bounds rows of the tensor copy
+    if (!two_ffts && rows_out != L) return false;
+    if ((reinterpret_cast<uintptr_t>(x) & 15) || (xcs & 1) || xcs < rows_in) return false;
+    return encode_tiled_fn() != nullptr;
+    (void)y; (void)ycs;
+#endif
+}
+
+// L = 2^20 complex64, column-major, no chirp: every pass in ONE persistent launch (fft_v32p.cuh)
+int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes,
+                         cudaStream_t st) const {
+#ifdef FMB_EMULATE
+    return FMB_ERR_NOTIMPL;
+#else
+    typedef float2 C;
+    static const long hint_on = env_long("FMB_V32P_HINTS", 1);
+    const bool bwd = direction == FMB_BACKWARD;
+    const int64_t rows_in = bwd ? n_out : n_in, rows_out = bwd ? n_in : n_out;
+    const int R1 = 1024, R2 = 1024;
+    const V32PGeom f = v32p_geom(M, L, two_ffts);
+    if (ws == nullptr || ws_bytes < f.counter_bytes + f.ring_bytes) {
+        set_error("workspace too small: need %lld bytes", (long long)(f.counter_bytes + f.ring_bytes));
+        return FMB_ERR_WORKSPACE;
+    }
+    FMB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)f.counter_bytes, st));
+    V32PArgs g;
+    memset(&g, 0, sizeof(g));
+    g.npass = f.npass; g.ncols = (int)M; g.slab_cols = f.slab_cols; g.nslabs = (int)f.nslabs;
+    g.delay = f.delay; g.nslot = f.nslot; g.mix = f.mix;
+    g.tiles = f.tiles; g.items_per_step = f.items_per_step;
+    g.total_items = (unsigned)((f.nslabs + (int64_t)(f.npass - 1) * f.delay) * f.items_per_step);
+    g.slot_stride = (long long)f.slab_cols * L;
+    g.y_slab_stride = (long long)f.slab_cols * ycs;
+    g.L = L;
+    g.done = (unsigned *)ws;
+    g.ring = (C *)((char *)ws + f.counter_bytes);
+    // L2 policies (createpolicy encodings): x is read once -> evict first; the ring is the working set -> evict last
+    g.hint_x = hint_on ? 0x12F0000000000000ull : 0x1000000000000000ull;
+    g.hint_ring = hint_on ? 0x14F0000000000000ull : 0x1000000000000000ull;
+    FastArgs<C> base;
+    memset(&base, 0, sizeof(base));
+    base.twL = (const C *)d.twL.p; base.twH = (const C *)d.twH.p; base.tw_shift = d.tw_shift;
+    base.tw_mask = (unsigned)(((int64_t)1 << d.tw_shift) - 1);
+    base.I = 1024; base.logI = 10;
+    {   // pass A: length R1 over n = f*R2 + i; ring[k1*R2 + i] * W^{i k1}
+        FastArgs<C> a = base;
+        a.out_cs = L; a.out_ks = R2; a.out_is = 1;
+        a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[0].p;
+        g.pass[0] = a;
+    }
+    int variant;
+    if (!two_ffts) {
+        FastArgs<C> a = base;                       // pass B: lines k1 contiguous in the ring; y[k1 + R1 k2]
+        a.out = (C *)y; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
+        a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
+        a.tw = (const C *)d.twV[1].p;
+        g.pass[1] = a;
+        variant = bwd ? VP_FC : VP_F;
+    } else {
+        FastArgs<C> a = base;                       // pass B': in place on the lines k1 of the ring
+        a.out_cs = L; a.out_ks = 1; a.out_is = R2;
+        a.mid = (const C *)d.mid.p; a.mid_is = R2;
+        a.tw = (const C *)d.twV[1].p; a.twS = (const C *)d.twS32[1].p;
+        g.pass[1] = a;
+        FastArgs<C> c = base;                       // pass C: length R1 over k1, lines m2; y[m1*R2 + m2]
+        c.out = (C *)y; c.out_cs = ycs; c.out_ks = R2; c.out_is = 1;
+        c.out_n = (int)rows_out; c.out_lk = R2; c.out_li = 1;
+        c.tw = (const C *)d.twV[0].p;
+        g.pass[2] = c;
+        variant = (bwd ? VP_CVC_N : VP_CV_N) + (rows_out == L ? 0 : 1);
+    }
+    CUtensorMap mx, mr;
+    int rc;
+    if ((rc = v32p_tensor_map(&mx, x, rows_in, xcs, M))) return rc;
+    if ((rc = v32p_tensor_map(&mr, g.ring, L, L, (int64_t)f.nslot * f.slab_cols))) return rc;
+    rc = launch_v32p_f(variant, g, mx, mr, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32p_c0(variant, g, mx, mr, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32p_c1(variant, g, mx, mr, st);
+    if (rc == FMB_ERR_NOTIMPL) set_error("V32P path: unknown variant %d", variant);
+    return rc;
+#endif
+}
+
 // ------------------------------------------------------------------------------------------- fused persistent path
 int launch_fused_f32_8_8(int variant, const FusedArgs<float2> &g, cudaStream_t st);
 int launch_fused_f32_8_9(int variant, const FusedArgs<float2> &g, cudaStream_t st);
@@ -855,6 +1019,7 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
             return FMB_ERR_WORKSPACE;
         }
         if (fused_ok<C>()) return run_fused<C>(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
+        if (v32_ok(sizeof(C)) && v32p_ok(direction, x, xcs, y, ycs)) return run_v32p(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
         if (v32_ok(sizeof(C))) return run_v32(d, direction, x, xcs, y, ycs, M, ws, st);
         return run_fast<C>(d, direction, x, xcs, y, ycs, M, ws, st);
     }

@@ -65,6 +65,10 @@ struct ConvEngine {
     int run_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const;
     bool v32_ok(size_t csize) const;
     int run_v32(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const;
+    bool v32p_ok(int direction, const void *x, int64_t xcs, const void *y, int64_t ycs) const;
+    int run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes,
+                 cudaStream_t st) const;
+    int64_t v32p_workspace_bytes(int64_t M) const;
     template <typename C> bool fused_ok() const;
     template <typename C>
     int run_fused(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes,
