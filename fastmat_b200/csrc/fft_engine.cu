@@ -276,7 +276,7 @@ int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
         slab_plan(M, csize, true, cols, ns);
         int64_t w = std::max(generic, (int64_t)cols * ns * L * (int64_t)csize);
         if (kron_a == 0) w = std::max(w, fused_workspace_bytes(M, csize));
-        if (kron_a == 0 && csize == sizeof(float2)) w = std::max(w, v32p_workspace_bytes(M));
+        if (csize == sizeof(float2)) w = std::max(w, v32p_workspace_bytes(M));
         return w;
     }
     return generic;
@@ -684,12 +684,12 @@ int launch_v32p_c1(int variant, const V32PArgs &g, const CUtensorMap &mx, const 
 
 struct V32PGeom { int slab_cols, delay, nslot, npass, mix; int64_t nslabs, counter_bytes, ring_bytes; unsigned tiles, items_per_step; };
 static V32PGeom v32p_geom(int64_t M, int64_t L, bool two) {
-    static const long slab_env = env_long("FMB_V32P_SLAB", 2), delay_env = env_long("FMB_V32P_DELAY", 0),
-                      mix_env = env_long("FMB_V32P_MIX", 1);
+    static const long slab_env = env_long("FMB_V32P_SLAB", 0), delay_env = env_long("FMB_V32P_DELAY", 0),
+                      mix_env = env_long("FMB_V32P_MIX", 0);
     V32PGeom f;
     f.npass = two ? 3 : 2;
     f.mix = mix_env ? 1 : 0;
-    f.slab_cols = (int)std::max<long>(1, std::min<long>(slab_env, 64));
+    f.slab_cols = slab_env > 0 ? (int)std::min<long>(slab_env, 64) : (two ? 2 : 1);      // as measured (tools/check_v32p.py)
     f.tiles = (unsigned)f.slab_cols * 128u;
     f.items_per_step = (unsigned)f.npass * f.tiles;
     // Correctness does not depend on D (fft_v32p.cuh); speed does: a tile is requested up to three items per CTA ahead of
@@ -752,8 +752,12 @@ bool ConvEngine::v32p_ok(int direction, const void *x, int64_t xcs, const void *
 #ifdef FMB_EMULATE
     return false;
 #else
+    // 1 (default): the plain 1-D transform only (measured +8..18 % over the per-pass kernels); 2: convolutions and the 2-D
+    // transform too - correct (bit-identical, tests/test_gpu_parity.py) but measured slower so far: passes whose lines
+    // are contiguous gain nothing from the asynchronous tile fetch and pay one more shared-memory read
     static const long on = env_long("FMB_V32P", 1);
-    if (!on || kron_a > 0 || !pre.empty() || !post.empty()) return false;
+    if (!on || !pre.empty() || !post.empty()) return false;
+    if ((two_ffts || kron_a > 0) && on < 2) return false;
     const int64_t rows_in = direction == FMB_BACKWARD ? n_out : n_in, rows_out = direction == FMB_BACKWARD ? n_in : n_out;
     if (rows_in <= 0 || rows_in % 1024 != 0) return false;              // zero padding = out-of-bounds rows of the tensor copy
     if (!two_ffts && rows_out != L) return false;
@@ -806,7 +810,14 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
         g.pass[0] = a;
     }
     int variant;
-    if (!two_ffts) {
+    if (kron_a > 0) {
+        FastArgs<C> a = base;                       // 2-D transform: second pass over i2 (contiguous), natural order out
+        a.out = (C *)y; a.out_cs = ycs; a.out_ks = 1; a.out_is = R2;
+        a.out_n = (int)L; a.out_lk = 1; a.out_li = R2;
+        a.tw = (const C *)d.twV[1].p;
+        g.pass[1] = a;
+        variant = bwd ? VP_KC : VP_K;
+    } else if (!two_ffts) {
         FastArgs<C> a = base;                       // pass B: lines k1 contiguous in the ring; y[k1 + R1 k2]
         a.out = (C *)y; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
         a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;

@@ -5,6 +5,8 @@ size-independent properties at the BASELINE sizes.
 Tolerance (BASELINE.json north_star): max|y - y_ref| <= tol * ||x||_2 * log2(N) per column with tol = 1e-5 for
 complex64/float32 and 1e-12 for complex128/float64; integer Hadamard / Permutation / Partial are bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -622,3 +624,82 @@ def test_cuda_graph_capture_of_pipelined_apply(fm):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(y, eager * 2.0) or float((y - eager * 2.0).abs().max()) <= 1e-6 * float(eager.abs().max())
+
+
+# ------------------------------------------------------------------------------------------- persistent TMA pipeline (V32P)
+_V32P_DUMP = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import fastmat_b200 as fm
+N = 1 << 20
+rng = np.random.default_rng(0)
+g = torch.Generator(device='cuda').manual_seed(11)
+c = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
+def crandn(m, n):
+    return torch.complex(torch.randn((m, n), device='cuda', generator=g), torch.randn((m, n), device='cuda', generator=g)).t()
+xs = crandn(11, N)                                   # ragged last slab for 2-column slabs
+C, F = fm.Circulant(c), fm.Fourier(N)
+K = fm.Kron(fm.Fourier(1024), fm.Fourier(1024))
+nt = N // 2
+T = fm.Toeplitz(c[:nt].copy(), c[nt:2 * nt - 1].copy())
+xt = crandn(5, nt)
+res = {}
+l0 = fm.launch_count()
+for name, fn, x in (('circ_f', C.forward, xs), ('circ_b', C.backward, xs), ('four_f', F.forward, xs), ('four_b', F.backward, xs),
+                    ('toep_f', T.forward, xt), ('toep_b', T.backward, xt), ('four_1', F.forward, xs[:, 3].contiguous()),
+                    ('circ_view', C.forward, xs[:, 2:9]), ('kron_f', K.forward, xs), ('kron_b', K.backward, xs)):
+    res[name] = fn(x).cpu()
+res['launches'] = fm.launch_count() - l0
+torch.save(res, sys.argv[1])
+print('dumped')
+'''
+
+
+def test_v32p_persistent_tma_pipeline_bit_identical_to_per_pass_kernels(fm, tmp_path):
+    """fft_v32p.cuh (one persistent launch, tiles requested by TMA ahead of the arithmetic, passes chained through global
+    completion counters) executes the same butterflies in the same order per column as the per-pass V32 kernels: outputs
+    must be BIT-identical for plain transforms (default path) and, opted in with FMB_V32P=2, for convolutions - including
+    a ragged last slab, zero padding done by out-of-bounds rows of the tensor map (Toeplitz), single columns, column
+    views - and the whole apply is one kernel launch."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    outs = {}
+    for mode in ('0', '1', '2'):
+        path = str(tmp_path / ('v32p_%s.pt' % mode))
+        e = dict(os.environ)
+        e['FMB_V32P'] = mode
+        r = subprocess.run([sys.executable, '-c', _V32P_DUMP, path], cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[mode] = torch.load(path)
+    for mode in ('1', '2'):
+        for k, ref in outs['0'].items():
+            if k != 'launches':
+                assert torch.equal(ref, outs[mode][k]), (mode, k)
+    # per-pass: 3 (2) launches per slab; persistent: one launch per plain transform (mode 1), one per apply (mode 2)
+    assert outs['2']['launches'] <= 12, outs['2']['launches']          # 10 applies (+ a layout copy for the column view)
+    assert outs['0']['launches'] > outs['1']['launches'] > outs['2']['launches']
+
+
+def test_v32p_apply_in_cuda_graph(fm):
+    """The persistent launch (memset of the completion counters + one kernel taking two tensor maps by value) can be
+    captured in a CUDA graph and replayed on new data."""
+    n, m = 2 ** 20, 6
+    F = fm.Fourier(n)
+    g = torch.Generator(device='cuda').manual_seed(8)
+    x = torch.complex(torch.randn((m, n), device='cuda', generator=g), torch.randn((m, n), device='cuda', generator=g)).t()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            y = F.forward(x)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        y = F.forward(x)
+    eager = F.forward(x).clone()
+    x.mul_(2.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(y, eager * 2.0)
