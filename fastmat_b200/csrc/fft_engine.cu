@@ -752,12 +752,13 @@ bool ConvEngine::v32p_ok(int direction, const void *x, int64_t xcs, const void *
 #ifdef FMB_EMULATE
     return false;
 #else
-    // 1 (default): the plain 1-D transform only (measured +8..18 % over the per-pass kernels); 2: convolutions and the 2-D
-    // transform too - correct (bit-identical, tests/test_gpu_parity.py) but measured slower so far: passes whose lines
-    // are contiguous gain nothing from the asynchronous tile fetch and pay one more shared-memory read
+    // 1 (default): plain transforms (1-D four-step and Kron's 2-D: measured +16..19 % over the per-pass kernels);
+    // 2: convolutions too - correct (bit-identical, tests/test_gpu_parity.py) but not faster so far: the middle pass is
+    // bound by arithmetic and shared memory, gains nothing from the asynchronous fetch of its (contiguous) lines and
+    // pays one more shared-memory read for it
     static const long on = env_long("FMB_V32P", 1);
     if (!on || !pre.empty() || !post.empty()) return false;
-    if ((two_ffts || kron_a > 0) && on < 2) return false;
+    if (two_ffts && on < 2) return false;
     const int64_t rows_in = direction == FMB_BACKWARD ? n_out : n_in, rows_out = direction == FMB_BACKWARD ? n_in : n_out;
     if (rows_in <= 0 || rows_in % 1024 != 0) return false;              // zero padding = out-of-bounds rows of the tensor copy
     if (!two_ffts && rows_out != L) return false;

@@ -34,7 +34,7 @@
 
 namespace fmb {
 
-constexpr int V32P_NT = 576, V32P_NBUF = 3;                                    // 16 compute warps + requester + signaller
+constexpr int V32P_NT = 640, V32P_NBUF = 3;                // 16 compute warps + one warpgroup for requester and signaller
 constexpr unsigned V32P_TILE_BYTES = 65536;                                     // 8 lines x 1024 complex64
 constexpr size_t V32P_BUF = V32_SMEM;                                           // 67712 = 529 * 128
 constexpr size_t V32P_CTRL = 256;                                               // mbarriers and counters, see v32p_kernel
@@ -265,7 +265,7 @@ __device__ __forceinline__ void v32p_tile(const FastArgs<float2> &a, float2 *con
 }
 
 template <unsigned OA, unsigned OB, unsigned OC>
-__global__ void __maxnreg__(112)
+__global__ void __launch_bounds__(V32P_NT, 1)
 v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_ring) {
     typedef float2 C;
     constexpr bool CONV = OC != 0;
@@ -273,22 +273,27 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
     extern __shared__ unsigned char v32p_smem_raw[];
     unsigned char *const base = v32p_smem_raw + ((128u - (v32p_smem_u32(v32p_smem_raw) & 127u)) & 127u);
     const unsigned base_s = v32p_smem_u32(base);
-    // control block: full[3] mbarriers (TMA completion) | req[3]: items requested into buffer j so far (+1) |
-    // handed[16], stored[16]: per compute warp, how many of its items have handed their buffer back / issued their stores
+    // control block: full[3][2] mbarriers (TMA completion) | handed[16], stored[16]: per compute warp, how many of its
+    // items have handed their buffer back / issued their stores.
+    // The k-th use of buffer j completes on full[j][k & 1] (phase k >> 1).  try_wait.parity cannot tell "phase not started"
+    // from "completed two phases ago", so a warp must only test a barrier whose PREVIOUS phase it has consumed itself:
+    // consecutive uses of a buffer alternate between the two groups, uses k and k - 2 belong to the same group.
     const unsigned ctrl = base_s + (unsigned)(V32P_NBUF * V32P_BUF);
-    const unsigned full_s = ctrl, req_s = ctrl + 32, handed_s = ctrl + 64, stored_s = ctrl + 128;
+    const unsigned full_s = ctrl, handed_s = ctrl + 64, stored_s = ctrl + 128;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (tid < 64) reinterpret_cast<unsigned *>(base + V32P_NBUF * V32P_BUF)[tid] = 0u;
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int j = 0; j < V32P_NBUF; ++j) v32p_mbar_init(full_s + 8 * j, 1);
+        for (int j = 0; j < 2 * V32P_NBUF; ++j) v32p_mbar_init(full_s + 8 * j, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
     const unsigned G = gridDim.x;
     const unsigned nloc = g.total_items > blockIdx.x ? (g.total_items - blockIdx.x + G - 1) / G : 0u;
 
+    // (register files are allocated in units of four warps: 18 warps cost as much as 20, i.e. 96 registers per thread)
+    if (warp > 17) return;
     if (warp == 16) {
         // ------------------------------------------------------------------ requester
         for (unsigned n = 0; n < nloc; ++n) {
@@ -306,8 +311,8 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
             }
             if (lane == 0) {
                 while (!v32p_ready<CONV>(g, it)) __nanosleep(64);
-                v32p_request<CONV>(g, &map_x, &map_ring, it, base_s + j * (unsigned)V32P_BUF, full_s + 8 * j);
-                v32p_st_rel(req_s + 4 * j, n + 1);
+                v32p_request<CONV>(g, &map_x, &map_ring, it, base_s + j * (unsigned)V32P_BUF,
+                                   full_s + 8 * (2 * j + ((n / V32P_NBUF) & 1u)));
             }
             __syncwarp();
         }
@@ -337,11 +342,8 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
         const V32PItem it = v32p_decode(g, blockIdx.x + n * G);
         const unsigned j = n % V32P_NBUF, k = n >> 1;
         C *const buf = reinterpret_cast<C *>(base + j * V32P_BUF);
-        // the barrier phase of item n exists only once item n has been requested (parity alone cannot tell phases
-        // n/3 and n/3 + 2 apart, and nothing else keeps a fast warp from running that far ahead of the requester)
-        if (lane == 0) while (v32p_ld_acq(req_s + 4 * j) < n + 1) { }
-        __syncwarp();
-        v32p_mbar_wait(full_s + 8 * j, (n / V32P_NBUF) & 1u);
+        const unsigned use = n / V32P_NBUF;
+        v32p_mbar_wait(full_s + 8 * (2 * j + (use & 1u)), (use >> 1) & 1u);
         auto handback = [&]() {
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             __syncwarp();
@@ -366,7 +368,9 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
 }
 
 // ---- variants (fft_engine.cu: run_v32p)
-enum V32PVariant { VP_F = 0, VP_FC = 1, VP_CV_N = 2, VP_CV_M = 3, VP_CVC_N = 4, VP_CVC_M = 5 };
+enum V32PVariant { VP_F = 0, VP_FC = 1, VP_CV_N = 2, VP_CV_M = 3, VP_CVC_N = 4, VP_CVC_M = 5, VP_K = 6, VP_KC = 7 };
+constexpr unsigned V32P_K_A = FO_LOAD_T | FO_STORE_T, V32P_K_AC = V32P_K_A | FO_IN_CONJ;     // Kron(Fourier, Fourier): no twiddle,
+constexpr unsigned V32P_K_B = 0u, V32P_K_BC = FO_OUT_CONJ;                                    // natural order, all rows kept
 
 template <unsigned OA, unsigned OB, unsigned OC>
 int launch_v32p_variant(const V32PArgs &g, const CUtensorMap &mx, const CUtensorMap &mr, cudaStream_t st) {

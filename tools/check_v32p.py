@@ -66,16 +66,17 @@ def child(out, cols):
 def main():
     import torch
     cols = int(os.environ.get('CHECK_COLS', '512'))
-    on = {'FMB_V32P': '2'}
+    on = {'FMB_V32P': '2'}                 # persistent path for convolutions too (default: plain transforms only)
     configs = [('v32 per-pass (reference)', {'FMB_V32P': '0'}),
-               ('v32p defaults (conv: slab 2, direct middle-pass loads; plain: slab 1)', dict(on)),
-               ('v32p middle pass through TMA', dict(on, FMB_V32P_MLDG='0')),
-               ('v32p slab=2 delay=2', dict(on, FMB_V32P_SLAB='2', FMB_V32P_DELAY='2')),
+               ('v32p defaults (conv: slab 2; plain: slab 1; blocked order)', dict(on)),
                ('v32p slab=1', dict(on, FMB_V32P_SLAB='1')),
-               ('v32p slab=1 ahead=8', dict(on, FMB_V32P_SLAB='1', FMB_V32P_AHEAD='8')),
-               ('v32p slab=1 ahead=3', dict(on, FMB_V32P_SLAB='1', FMB_V32P_AHEAD='3')),
+               ('v32p slab=2', dict(on, FMB_V32P_SLAB='2')),
                ('v32p slab=3', dict(on, FMB_V32P_SLAB='3')),
-               ('v32p slab=2 mix=1', dict(on, FMB_V32P_SLAB='2', FMB_V32P_MIX='1'))]
+               ('v32p ahead=3', dict(on, FMB_V32P_AHEAD='3')),
+               ('v32p ahead=8', dict(on, FMB_V32P_AHEAD='8')),
+               ('v32p interleaved order', dict(on, FMB_V32P_MIX='1')),
+               ('v32p no L2 hints', dict(on, FMB_V32P_HINTS='0')),
+               ('v32p L2 promotion 128 B', dict(on, FMB_V32P_PROMO='2'))]
     extra = os.environ.get('CHECK_ONLY')
     if extra:
         configs = [configs[0]] + [c for c in configs[1:] if extra in c[0]]
