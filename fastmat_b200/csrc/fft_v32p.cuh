@@ -299,21 +299,22 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
         for (unsigned n = 0; n < nloc; ++n) {
             const V32PItem it = v32p_decode(g, blockIdx.x + n * G);
             const unsigned j = n % V32P_NBUF;
+            // producers first (normally long done: one poll through L2), so that nothing but the issue itself is left to
+            // do at the moment the buffer comes back
+            if (lane == 0) while (!v32p_ready<CONV>(g, it)) __nanosleep(64);
             if (n >= (unsigned)V32P_NBUF) {           // buffer j was used by item n - 3: all eight warps of its group done with it?
                 const unsigned prev = n - V32P_NBUF, gp = prev & 1u, kp = prev >> 1;
                 for (;;) {
                     const unsigned cnt = lane < 16 ? v32p_ld_acq(handed_s + 4 * lane) : 0xffffffffu;
                     const bool ok = (lane >> 3) != gp || cnt > kp;
                     if (__all_sync(0xffffffffu, ok)) break;
-                    __nanosleep(64);
+                    __nanosleep(20);
                 }
                 __syncwarp();                         // lane 0 inherits what the other lanes acquired
             }
-            if (lane == 0) {
-                while (!v32p_ready<CONV>(g, it)) __nanosleep(64);
+            if (lane == 0)
                 v32p_request<CONV>(g, &map_x, &map_ring, it, base_s + j * (unsigned)V32P_BUF,
                                    full_s + 8 * (2 * j + ((n / V32P_NBUF) & 1u)));
-            }
             __syncwarp();
         }
         return;

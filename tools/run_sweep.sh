@@ -1,12 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q -k "v32p" > gpurun_out/pytest_v32p.log 2>&1; tail -2 gpurun_out/pytest_v32p.log
 {
+  FMB_V32P=0 timeout 200 python tools/sweep_v32p.py fourier 1024
+  for h in 0 1 2 3; do FMB_V32P_STHINT=$h timeout 200 python tools/sweep_v32p.py fourier 1024; done
+  for h in 0 3; do FMB_V32P_STHINT=$h timeout 200 python tools/sweep_v32p.py kron 1024; done
   FMB_V32P=0 timeout 200 python tools/sweep_v32p.py circulant 1024
-  FMB_V32P=2 timeout 200 python tools/sweep_v32p.py circulant 1024
-  FMB_V32P=2 FMB_V32P_MLDG=1 timeout 200 python tools/sweep_v32p.py circulant 1024
-  FMB_V32P=2 FMB_V32P_MLDG=1 FMB_V32P_AHEAD=3 timeout 200 python tools/sweep_v32p.py circulant 1024
-  FMB_V32P=2 FMB_V32P_MLDG=1 FMB_V32P_SLAB=1 timeout 200 python tools/sweep_v32p.py circulant 1024
-  FMB_V32P=2 FMB_V32P_MLDG=1 FMB_V32P_SLAB=4 timeout 200 python tools/sweep_v32p.py circulant 1024
-  FMB_V32P=2 FMB_V32P_MLDG=1 FMB_V32P_MIX=1 timeout 200 python tools/sweep_v32p.py circulant 1024
+  for h in 0 1 3; do FMB_V32P=2 FMB_V32P_STHINT=$h timeout 200 python tools/sweep_v32p.py circulant 1024; done
 } 2>&1 | grep -v -i warn | tee gpurun_out/sweep_v32p.log
-CHECK_COLS=64 CHECK_ONLY=defaults FMB_V32P_MLDG=1 timeout 300 python tools/check_v32p.py 2>&1 | grep -E "^==|MISMATCH|CHECK|identical|TIMEOUT|FAILED"
