@@ -62,14 +62,16 @@ __device__ __forceinline__ void v32p_mbar_init(unsigned bar, unsigned count) {
 __device__ __forceinline__ void v32p_mbar_expect_tx(unsigned bar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+// blocking wait; the time hint lets the hardware park the warp instead of returning at once (a bare try_wait loop
+// retried ~200 times per tile and took a quarter of all issued instructions in the convolution kernel)
 __device__ __forceinline__ void v32p_mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "V32P_WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra V32P_DONE_%=;\n\t"
         "bra V32P_WAIT_%=;\n\t"
-        "V32P_DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+        "V32P_DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
 }
 // 3-D box {8 elements, 256 rows, 1 column} of a tensor of 8-byte elements -> 16 KB of shared memory
 __device__ __forceinline__ void v32p_tma_box(unsigned dst, const CUtensorMap *map, unsigned bar, int c0, int c1, int c2,

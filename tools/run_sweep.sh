@@ -3,8 +3,10 @@ mkdir -p gpurun_out
 timeout 600 python -m pytest tests -m gpu -x -q -k "v32p" > gpurun_out/pytest_v32p.log 2>&1; tail -2 gpurun_out/pytest_v32p.log
 {
   FMB_V32P=0 timeout 200 python tools/sweep_v32p.py fourier 1024
-  for h in 0 1 2 3; do FMB_V32P_STHINT=$h timeout 200 python tools/sweep_v32p.py fourier 1024; done
-  for h in 0 3; do FMB_V32P_STHINT=$h timeout 200 python tools/sweep_v32p.py kron 1024; done
+  timeout 200 python tools/sweep_v32p.py fourier 1024
+  timeout 200 python tools/sweep_v32p.py kron 1024
   FMB_V32P=0 timeout 200 python tools/sweep_v32p.py circulant 1024
-  for h in 0 1 3; do FMB_V32P=2 FMB_V32P_STHINT=$h timeout 200 python tools/sweep_v32p.py circulant 1024; done
+  FMB_V32P=2 timeout 200 python tools/sweep_v32p.py circulant 1024
+  FMB_V32P=2 FMB_V32P_SLAB=1 timeout 200 python tools/sweep_v32p.py circulant 1024
+  FMB_V32P=2 FMB_V32P_AHEAD=3 timeout 200 python tools/sweep_v32p.py circulant 1024
 } 2>&1 | grep -v -i warn | tee gpurun_out/sweep_v32p.log
