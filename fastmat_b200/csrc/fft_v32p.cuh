@@ -3,12 +3,14 @@
 //
 // The per-pass kernels of fft_v32.cuh spend most of their time waiting: a CTA loads its tile (32 LDG per thread), then
 // computes, then stores, and with 128 registers per thread only two CTAs fit on an SM, so the load latency of one tile
-// is hidden by at most one other tile.  Here one CTA of 18 warps stays resident per SM:
+// is hidden by at most one other tile.  Here one CTA of 18 working warps stays resident per SM
+// (launched as 20: register files are allocated per four warps, which leaves 96 registers per thread - enough):
 //
 //   * warps 0-7 and 8-15 are two compute "groups" (256 threads = 8 lines x 32 threads, the V32 tile shape) working on
 //     different tiles.  The tile data does not pass through registers on the way in: it is waited for on an mbarrier
 //     and read from one of THREE 66 KB shared-memory buffers, which is then reused in place as the exchange buffer
-//     between the two radix-32 stages.  Compute warps never wait for anything but their data.
+//     between the two radix-32 stages.  Compute warps never wait for anything but their data (mbarrier.try_wait; two
+//     barriers per buffer, see v32p_kernel).
 //   * warp 16 (one lane) is the requester: as soon as all eight warps of a group have handed a buffer back (per-warp
 //     counters in shared memory) it waits for the next tile's producers (global counters, see below) and issues the
 //     bulk-tensor copies - cp.async.bulk.tensor, 4 boxes of 256 rows x 64 B, for the strided passes (zero padding =
