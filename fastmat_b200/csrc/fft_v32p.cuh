@@ -55,6 +55,7 @@ struct V32PArgs {
     float2 *ring;
     unsigned *done;                // [npass][nslabs] completed tiles
     unsigned long long hint_x, hint_ring;      // L2 cache policies of the two kinds of tile request
+    int prefetch_x;                            // > 0: pull the x tile of the item that many requests ahead into L2
 };
 
 __device__ __forceinline__ unsigned v32p_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -81,6 +82,9 @@ __device__ __forceinline__ void v32p_tma_box(unsigned dst, const CUtensorMap *ma
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;"
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "l"(hint) : "memory");
+}
+__device__ __forceinline__ void v32p_tma_prefetch_box(const CUtensorMap *map, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global [%0, {%1, %2, %3}];" ::"l"(map), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
 __device__ __forceinline__ void v32p_bulk_line(unsigned dst, const void *src, unsigned bytes, unsigned bar, unsigned long long hint) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
@@ -316,9 +320,20 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
                 }
                 __syncwarp();                         // lane 0 inherits what the other lanes acquired
             }
-            if (lane == 0)
+            if (lane == 0) {
                 v32p_request<CONV>(g, &map_x, &map_ring, it, base_s + j * (unsigned)V32P_BUF,
                                    full_s + 8 * (2 * j + ((n / V32P_NBUF) & 1u)));
+                // x comes from HBM: start pulling the tile of a later pass-A item into L2 now (the request itself can
+                // only be made when a buffer is free, half a tile time before the data is needed)
+                if (g.prefetch_x > 0 && n + (unsigned)g.prefetch_x < nloc) {
+                    const V32PItem nx = v32p_decode(g, blockIdx.x + (n + (unsigned)g.prefetch_x) * G);
+                    if (nx.compute && nx.p == 0) {
+                        const int c2 = nx.slab * g.slab_cols + (int)(nx.tile >> 7), c0 = (int)((nx.tile & 127u) << V32_LOGT);
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) v32p_tma_prefetch_box(&map_x, c0, 256 * q, c2);
+                    }
+                }
+            }
             __syncwarp();
         }
         return;
