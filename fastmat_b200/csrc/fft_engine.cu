@@ -799,10 +799,6 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
     // L2 policies (createpolicy encodings): x is read once -> evict first; the ring is the working set -> evict last
     g.hint_x = hint_on ? 0x12F0000000000000ull : 0x1000000000000000ull;
     g.hint_ring = hint_on ? 0x14F0000000000000ull : 0x1000000000000000ull;
-    {
-        static const long pair = env_long("FMB_V32P_PAIR", 0);
-        g.pair = pair ? 1 : 0;
-    }
     FastArgs<C> base;
     memset(&base, 0, sizeof(base));
     base.twL = (const C *)d.twL.p; base.twH = (const C *)d.twH.p; base.tw_shift = d.tw_shift;

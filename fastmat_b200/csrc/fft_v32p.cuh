@@ -55,7 +55,6 @@ struct V32PArgs {
     float2 *ring;
     unsigned *done;                // [npass][nslabs] completed tiles
     unsigned long long hint_x, hint_ring;      // L2 cache policies of the two kinds of tile request
-    int pair;                                  // 1: the two groups of a CTA work on adjacent tiles (see v32p_item)
 };
 
 __device__ __forceinline__ unsigned v32p_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -98,17 +97,6 @@ __device__ __forceinline__ unsigned v32p_ld_acq(unsigned addr) {
 }
 __device__ __forceinline__ void v32p_st_rel(unsigned addr, unsigned v) {
     asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
-}
-
-// global index of the n-th item of CTA c (G CTAs).  Round robin by item, or by PAIRS of items: the two groups of a CTA then
-// work on adjacent tiles - the two 64-byte halves of the same 128-byte lines - at about the same time.
-__device__ __forceinline__ unsigned v32p_item(const int pair, unsigned n, unsigned c, unsigned G) {
-    return pair ? (((n >> 1) * G + c) << 1) + (n & 1u) : c + n * G;
-}
-__device__ __forceinline__ unsigned v32p_items_of_cta(const int pair, unsigned total, unsigned c, unsigned G) {
-    if (!pair) return total > c ? (total - c + G - 1) / G : 0u;
-    const unsigned pairs = total >> 1;                                  // total is even (128 tiles per column)
-    return pairs > c ? 2u * ((pairs - c + G - 1) / G) : 0u;
 }
 
 struct V32PItem { int p, slab; unsigned tile; bool in_range, compute; };
@@ -306,14 +294,14 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
     }
     __syncthreads();
     const unsigned G = gridDim.x;
-    const unsigned nloc = v32p_items_of_cta(g.pair, g.total_items, blockIdx.x, G);
+    const unsigned nloc = g.total_items > blockIdx.x ? (g.total_items - blockIdx.x + G - 1) / G : 0u;
 
     // (register files are allocated in units of four warps: 18 warps cost as much as 20, i.e. 96 registers per thread)
     if (warp > 17) return;
     if (warp == 16) {
         // ------------------------------------------------------------------ requester
         for (unsigned n = 0; n < nloc; ++n) {
-            const V32PItem it = v32p_decode(g, v32p_item(g.pair, n, blockIdx.x, G));
+            const V32PItem it = v32p_decode(g, blockIdx.x + n * G);
             const unsigned j = n % V32P_NBUF;
             // producers first (normally long done: one poll through L2), so that nothing but the issue itself is left to
             // do at the moment the buffer comes back
@@ -339,7 +327,7 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
     if (warp == 17) {
         // ------------------------------------------------------------------ signaller
         for (unsigned n = 0; n < nloc; ++n) {
-            const V32PItem it = v32p_decode(g, v32p_item(g.pair, n, blockIdx.x, G));
+            const V32PItem it = v32p_decode(g, blockIdx.x + n * G);
             const unsigned gs = n & 1u, k = n >> 1;
             for (;;) {
                 const unsigned cnt = lane < 16 ? v32p_ld_acq(stored_s + 4 * lane) : 0xffffffffu;
@@ -357,7 +345,7 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
     // ---------------------------------------------------------------------- compute groups
     const int group = tid >> 8, gt = tid & 255;
     for (unsigned n = group; n < nloc; n += 2) {
-        const V32PItem it = v32p_decode(g, v32p_item(g.pair, n, blockIdx.x, G));
+        const V32PItem it = v32p_decode(g, blockIdx.x + n * G);
         const unsigned j = n % V32P_NBUF, k = n >> 1;
         C *const buf = reinterpret_cast<C *>(base + j * V32P_BUF);
         const unsigned use = n / V32P_NBUF;
