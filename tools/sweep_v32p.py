@@ -18,6 +18,12 @@ if what == 'fourier':
     M = fm.Fourier(N)
 elif what == 'kron':
     M = fm.Kron(fm.Fourier(1024), fm.Fourier(1024))
+elif what == 'toeplitz':
+    rng = np.random.default_rng(0)
+    nt = N // 2
+    M = fm.Toeplitz((rng.standard_normal(nt) + 1j * rng.standard_normal(nt)).astype(np.complex64),
+                    (rng.standard_normal(nt - 1) + 1j * rng.standard_normal(nt - 1)).astype(np.complex64))
+    x = x[:nt].t().contiguous().t()
 else:
     rng = np.random.default_rng(0)
     M = fm.Circulant((rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64))
