@@ -14,6 +14,7 @@ from .Diag import Diag                                             # noqa: F401
 from .Partial import Partial                                       # noqa: F401
 from .Product import Product                                       # noqa: F401
 from .Sum import Sum                                               # noqa: F401
+from .LFSRCirculant import LFSRCirculant                         # noqa: F401
 from .Kron import Kron                                             # noqa: F401
 from .Blocks import Blocks                                         # noqa: F401
 from .BlockDiag import BlockDiag                                   # noqa: F401

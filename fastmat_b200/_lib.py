@@ -28,6 +28,9 @@ SIGNATURES = {
     'fmb_device_info': (ctypes.c_int, [ctypes.POINTER(ctypes.c_int)] * 3 + [ctypes.POINTER(ctypes.c_size_t)]),
     'fmb_find_optimal_fft_size': (c_i64, [c_i64, ctypes.c_int]),
     'fmb_fft_complexity': (ctypes.c_float, [c_i64]),
+    'fmb_lfsr_order': (ctypes.c_int, [ctypes.c_uint32]),
+    'fmb_lfsr_period': (c_i64, [ctypes.c_uint32, ctypes.c_uint32]),
+    'fmb_lfsr_sequences': (ctypes.c_int, [ctypes.c_uint32, ctypes.c_uint32, c_i64, c_vp, c_vp, c_vp]),
     'fmb_fourier_plan_create': (ctypes.c_int, [ctypes.POINTER(c_vp), c_i64, ctypes.c_int, ctypes.c_int]),
     'fmb_circulant_plan_create': (ctypes.c_int, [ctypes.POINTER(c_vp), c_vp, c_i64, ctypes.c_int, ctypes.c_int]),
     'fmb_toeplitz_plan_create': (ctypes.c_int, [ctypes.POINTER(c_vp), c_vp, c_i64, c_vp, c_i64, ctypes.c_int, ctypes.c_int]),

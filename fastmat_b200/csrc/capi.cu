@@ -285,6 +285,25 @@ int fmb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_byte
 int64_t fmb_find_optimal_fft_size(int64_t order, int max_stage) { return find_optimal_fft_size(order, max_stage); }
 float fmb_fft_complexity(int64_t n) { return fft_complexity(n); }
 
+int fmb_lfsr_order(uint32_t polynomial) { return lfsr_order(polynomial); }
+
+int64_t fmb_lfsr_period(uint32_t polynomial, uint32_t start) {
+    const int64_t p = lfsr_period(polynomial, start);
+    if (p == -1) set_error("Only polynomials of order 1 to 31 are supported.");          // LFSRCirculant.pyx:201-202
+    else if (p == -2) set_error("Initial state must be non-zero.");                       // :204-205
+    else if (p == -3) set_error("Register configuration produces invalid sequence.");     // :218-220
+    return p < 0 ? (int64_t)FMB_ERR_VALUE : p;
+}
+
+int fmb_lfsr_sequences(uint32_t polynomial, uint32_t start, int64_t n, uint32_t *gen_states, uint32_t *tap_states,
+                       int8_t *vec_c) {
+    const int order = lfsr_order(polynomial);
+    if (order > 31 || order < 1) { set_error("Only polynomials of order 1 to 31 are supported."); return FMB_ERR_VALUE; }
+    if (n < 0) { set_error("LFSR: negative sequence length"); return FMB_ERR_VALUE; }
+    lfsr_sequences(polynomial, start, n, gen_states, tap_states, vec_c);
+    return FMB_OK;
+}
+
 int fmb_fourier_plan_create(fmb_plan **out, int64_t order, int optimize, int max_stage) {
     FMB_GUARD_BEGIN
     if (!out) { set_error("null output pointer"); return FMB_ERR_VALUE; }

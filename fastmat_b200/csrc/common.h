@@ -130,6 +130,10 @@ struct PipeScope {
 // ---- planner (planner.cpp): fastmat/core/cmath.pyx:35-214
 int64_t find_optimal_fft_size(int64_t order, int max_stage);
 float fft_complexity(int64_t n);
+// ---- LFSR sequences (planner.cpp): fastmat/LFSRCirculant.pyx:28-48, :196-222, :277-395
+int lfsr_order(uint32_t polynomial);
+int64_t lfsr_period(uint32_t polynomial, uint32_t start);
+void lfsr_sequences(uint32_t polynomial, uint32_t start, int64_t n, uint32_t *gen_states, uint32_t *tap_states, int8_t *vec_c);
 
 // ---- Plan base
 struct PlanBase {

@@ -3,6 +3,7 @@
 // The reference keeps `remaining` and `complexity` in C floats; so does this file, because those roundings decide
 // padded sizes (e.g. the answer for 2^24+1 is 2^24) and hence the internal layout of Circulant / Toeplitz / Fourier.
 #include <cmath>
+#include <cstdint>
 
 #include "common.h"
 
@@ -51,6 +52,60 @@ float fft_complexity(int64_t n) {
     }
     if (nn > 1) complexity += (float)(nn + 1);
     return float_n * (complexity + 1);
+}
+
+// ---- LFSRCirculant host logic (fastmat/LFSRCirculant.pyx:28-48 step functions, :196-222 order / period checks,
+//      :277-314 states / vecC, :316-395 the two address sequences of _core).  Integer work, reproduced exactly.
+
+// Fibonacci step of the generator register: feedback = parity of (state & polynomial), shifted in at bit `order`.
+static inline uint32_t lfsr_gen_step(uint32_t state, uint32_t polynomial, uint32_t mask) {
+    if (__builtin_parity(state & polynomial)) state |= mask;
+    return state >> 1;
+}
+
+// Galois step of the tap (address) register: multiply by x modulo the polynomial.
+static inline uint32_t lfsr_tap_step(uint32_t state, uint32_t polynomial, uint32_t mask) {
+    state <<= 1;
+    if (state & mask) state ^= (polynomial | mask);
+    return state;
+}
+
+int lfsr_order(uint32_t polynomial) {
+    int order = 0;
+    uint32_t mask = 1;
+    while ((~mask & polynomial) > mask) { mask <<= 1; ++order; }
+    return order;
+}
+
+// period of the register, or -1 (order outside 1..31), -2 (zero start), -3 (sequence never returns to start)
+int64_t lfsr_period(uint32_t polynomial, uint32_t start) {
+    const int order = lfsr_order(polynomial);
+    if (order > 31 || order < 1) return -1;
+    const uint32_t mask = 1u << order;
+    start &= (mask - 1);
+    if (start == 0) return -2;
+    uint32_t state = lfsr_gen_step(start, polynomial, mask);
+    int64_t period = 1;
+    while (state != start) {
+        state = lfsr_gen_step(state, polynomial, mask);
+        ++period;
+        if (period >= (int64_t)mask || state == 0) return -3;
+    }
+    return period;
+}
+
+// n successive generator states from `start`, tap states from 1, and the +1/-1 output sequence (any may be null)
+void lfsr_sequences(uint32_t polynomial, uint32_t start, int64_t n, uint32_t *gen_states, uint32_t *tap_states,
+                    int8_t *vec_c) {
+    const uint32_t mask = 1u << lfsr_order(polynomial);
+    uint32_t g = start & (mask - 1), t = 1;
+    for (int64_t i = 0; i < n; ++i) {
+        if (gen_states) gen_states[i] = g & (mask - 1);
+        if (tap_states) tap_states[i] = t;
+        if (vec_c) vec_c[i] = (g & 1) ? -1 : 1;
+        g = lfsr_gen_step(g, polynomial, mask);
+        t = lfsr_tap_step(t, polynomial, mask);
+    }
 }
 
 }  // namespace fmb

@@ -76,6 +76,15 @@ int fmb_device_info(int *sm_count, int *cc_major, int *cc_minor, size_t *l2_byte
 int64_t fmb_find_optimal_fft_size(int64_t order, int max_stage);
 float fmb_fft_complexity(int64_t n);
 
+/* ---- host-side LFSR logic of LFSRCirculant (integer, exact): fastmat/LFSRCirculant.pyx:28-48 (lfsrGenStep /
+ *      lfsrTapStep), :196-222 (order and period, with the constructor's ValueErrors), :277-314 (states, vecC),
+ *      :316-395 (generator / tap address sequences of _core).  fmb_lfsr_period returns FMB_ERR_VALUE (< 0) with
+ *      the reference's message in fmb_last_error() for an invalid register.  Output pointers may be NULL.      */
+int fmb_lfsr_order(uint32_t polynomial);
+int64_t fmb_lfsr_period(uint32_t polynomial, uint32_t start);
+int fmb_lfsr_sequences(uint32_t polynomial, uint32_t start, int64_t n, uint32_t *gen_states, uint32_t *tap_states,
+                       int8_t *vec_c);
+
 /* ---- plan constructors (one per reference class on the path) -------------------------------------------- */
 
 /* Fourier(order, optimize, maxStage): fastmat/Fourier.pyx:63-161.  forward = unnormalised DFT along axis 0

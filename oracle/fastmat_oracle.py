@@ -418,3 +418,94 @@ def permutation_backward(sigma, x):
     x2, was1d = _as2d(x)
     tau = np.argsort(np.asarray(sigma))
     return _ret(x2[tau], was1d)
+
+
+# ----------------------------------------------------------------------------------------------- LFSRCirculant
+
+def lfsr_order(polynomial):
+    """fastmat/LFSRCirculant.pyx:191-196: index of the highest set bit of the characteristic polynomial."""
+    order, mask = 0, 1
+    while (~mask & polynomial) > mask:
+        mask <<= 1
+        order += 1
+    return order
+
+
+def lfsr_gen_step(state, polynomial, mask):
+    """fastmat/LFSRCirculant.pyx:31-40: Fibonacci step, feedback = parity(state & polynomial) enters at bit `order`."""
+    if bin(state & polynomial).count('1') & 1:
+        state |= mask
+    return state >> 1
+
+
+def lfsr_tap_step(state, polynomial, mask):
+    """fastmat/LFSRCirculant.pyx:42-48: Galois step (multiply by x modulo the polynomial)."""
+    state <<= 1
+    if state & mask:
+        state ^= (polynomial | mask)
+    return state
+
+
+def lfsr_period(polynomial, start):
+    """fastmat/LFSRCirculant.pyx:196-222 including the constructor's three ValueErrors."""
+    order = lfsr_order(polynomial)
+    if order > 31 or order < 1:
+        raise ValueError("Only polynomials of order 1 to 31 are supported.")
+    mask = 1 << order
+    start &= mask - 1
+    if start == 0:
+        raise ValueError("Initial state must be non-zero.")
+    state, period = lfsr_gen_step(start, polynomial, mask), 1
+    while state != start:
+        state = lfsr_gen_step(state, polynomial, mask)
+        period += 1
+        if period >= mask or state == 0:
+            raise ValueError("Register configuration produces invalid sequence.")
+    return period
+
+
+def lfsr_sequences(polynomial, start):
+    """Generator states, tap states (from 1) and the +1/-1 output over one period (:277-314, :343-395)."""
+    n = lfsr_period(polynomial, start)
+    mask = 1 << lfsr_order(polynomial)
+    g, t = start & (mask - 1), 1
+    gen, tap, vec = np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.int8)
+    for i in range(n):
+        gen[i], tap[i], vec[i] = g, t, (-1 if g & 1 else 1)
+        g = lfsr_gen_step(g, polynomial, mask)
+        t = lfsr_tap_step(t, polynomial, mask)
+    return gen, tap, vec
+
+
+def _lfsr_core(polynomial, start, x, flip_in, flip_out):
+    """fastmat/LFSRCirculant.pyx:316-395: scatter rows to the generator-state addresses of a zeroed 2^order buffer
+    (row 0 first, the remaining rows reversed when flip_in), Hadamard in the input's dtype, gather from the
+    tap-state addresses (row 0 first, remaining rows reversed when flip_out)."""
+    x2, was1d = _as2d(x)
+    gen, tap, _ = lfsr_sequences(polynomial, start)
+    n, order = gen.size, lfsr_order(polynomial)
+    assert x2.shape[0] == n
+    k = np.arange(n)
+    flipped = np.where(k == 0, 0, n - k)
+    data = np.zeros((1 << order, x2.shape[1]), dtype=x2.dtype)
+    data[gen] = x2[flipped if flip_in else k]
+    data = hadamard_forward(data, order)
+    y = np.empty_like(x2)
+    y[flipped if flip_out else k] = data[tap]
+    return _ret(y, was1d)
+
+
+def lfsr_circulant_forward(polynomial, start, x):
+    """fastmat/LFSRCirculant.pyx:398-401."""
+    return _lfsr_core(polynomial, start, x, True, False)
+
+
+def lfsr_circulant_backward(polynomial, start, x):
+    """fastmat/LFSRCirculant.pyx:403-406."""
+    return _lfsr_core(polynomial, start, x, False, True)
+
+
+def dense_lfsr_circulant(polynomial, start):
+    """fastmat/LFSRCirculant.pyx:409-437: columns are the rolled output sequence."""
+    _, _, vec = lfsr_sequences(polynomial, start)
+    return np.stack([np.roll(vec, i) for i in range(vec.size)], axis=1)
