@@ -338,6 +338,13 @@ def run_ours(args):
         Hd = fm.Hadamard(20)
         xf = torch.view_as_real(x.t().contiguous()).reshape(cols * 2, N).t()             # (2^20, 2048) float32, column-major
         rec('hadamard_forward_o20_f32', timed(lambda: Hd.forward(xf), k2, 3), xf.shape[1], 8.0 * N)
+        try:            # scatter -> FWHT(order 20) -> gather, three launches; 2 x 4 B x (2^20 - 1) per column
+            Ll = fm.LFSRCirculant((1 << 20) | (1 << 3) | 1, 1)
+            xl = xf[:N - 1, :1024].t().contiguous().t()
+            rec('lfsr_circulant_forward_o20_f32', timed(lambda: Ll.forward(xl), k2, 3), xl.shape[1], 8.0 * (N - 1))
+            del xl, Ll
+        except Exception as e:                                     # a secondary row must not take the headline down
+            extras['lfsr_circulant_forward_o20_f32'] = {'error': repr(e)}
         del xf
         Fb = fm.Fourier(1000003)
         xb = x[:1000003, :256].t().contiguous().t()
