@@ -1,4 +1,4 @@
-"""GPU parity of LFSRCirculant: class layer -> C-ABI (scatter, FWHT, gather kernels) against the
+"""(Named zz so that it runs after the parity suite of the headline path.)  GPU parity of LFSRCirculant: class layer -> C-ABI (scatter, FWHT, gather kernels) against the
 fixtures frozen from the real reference (tests/golden/golden_lfsr.npz) and the numpy oracle; all bit-exact (integer
 and small-integer-valued float inputs), plus the size-independent circulant properties on a 2^20-1 register."""
 import os
