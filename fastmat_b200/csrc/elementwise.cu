@@ -170,10 +170,62 @@ int diag_apply(const void *d_dev, int dt_d, int64_t n, int conj_d, const void *x
 
 template <template <typename> class K> struct BySize {};
 
+// Column-major operands (consecutive threads walk rows): one thread owns one selected row and carries it through CB
+// columns, so the index is read once per CB elements, the CB random accesses are independent (all in flight at once)
+// and there is no 64-bit division per element.  Blocks are ordered rows-first: the launch sweeps a group of CB columns
+// from top to bottom before it moves on, which keeps the randomly addressed side of the copy (CB columns) resident in
+// L2 while the other side streams.
+template <typename B, bool SCATTER, int CB> __global__ void __launch_bounds__(256) permute_cols_kernel(const __grid_constant__ EwParams p) {
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= p.n) return;
+    const long long i = __ldg((const long long *)p.d + r);
+    const B *src = (const B *)p.x + (SCATTER ? r : i) * p.xrs;
+    B *dst = (B *)p.y + (SCATTER ? i : r) * p.yrs;
+    for (long long c0 = (long long)blockIdx.y * CB; c0 < p.M; c0 += (long long)gridDim.y * CB) {
+        B v[CB];
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+            if (c0 + c < p.M) v[c] = src[(c0 + c) * p.xcs];
+#pragma unroll
+        for (int c = 0; c < CB; ++c)
+            if (c0 + c < p.M) dst[(c0 + c) * p.ycs] = v[c];
+    }
+}
+
+template <typename B, bool SCATTER> static int permute_cols_launch(const EwParams &p, cudaStream_t st) {
+#ifdef FMB_EMULATE
+    set_error("element-wise kernels are not emulated");
+    return FMB_ERR_NOTIMPL;
+#else
+    constexpr int CB = 4;
+    const long long groups = (p.M + CB - 1) / CB;
+    dim3 grid((unsigned)((p.n + 255) / 256), (unsigned)(groups < 65535 ? groups : 65535));
+    permute_cols_kernel<B, SCATTER, CB><<<grid, 256, 0, st>>>(p);
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+#endif
+}
+
+// FMB_EW_TILED=0 keeps the flat grid-stride kernels for column-major operands too (A/B runs)
+static bool ew_tiled(const EwParams &p) {
+    static const long on = getenv("FMB_EW_TILED") ? atol(getenv("FMB_EW_TILED")) : 1;
+    return on && !p.c_fastest && p.n * p.M > 0 && (p.n + 255) / 256 < 0x7fffffffLL;
+}
+
 int gather_apply(const void *idx_dev, int64_t nsel, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs,
                  int64_t M, int dtype, cudaStream_t st) {
     EwParams p = ew_params(nsel, M, x, xrs, xcs, y, yrs, ycs);
     p.d = idx_dev;
+    if (ew_tiled(p)) {
+        switch (dtype_size(dtype)) {
+            case 1: return permute_cols_launch<uint8_t, false>(p, st);
+            case 2: return permute_cols_launch<uint16_t, false>(p, st);
+            case 4: return permute_cols_launch<uint32_t, false>(p, st);
+            case 8: return permute_cols_launch<uint64_t, false>(p, st);
+            case 16: return permute_cols_launch<double2, false>(p, st);
+            default: set_error("Partial: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
+        }
+    }
     switch (dtype_size(dtype)) {
         case 1: FMB_EW_LAUNCH(gather_kernel<uint8_t>, p, st); break;
         case 2: FMB_EW_LAUNCH(gather_kernel<uint16_t>, p, st); break;
@@ -190,6 +242,16 @@ int scatter_apply(const void *idx_dev, int64_t nsel, int64_t ntotal, const void 
     EwParams z = ew_params(ntotal, M, nullptr, 0, 0, y, yrs, ycs);
     EwParams p = ew_params(nsel, M, x, xrs, xcs, y, yrs, ycs);
     p.d = idx_dev;
+    if (ew_tiled(p)) {
+        switch (dtype_size(dtype)) {
+            case 1: FMB_EW_LAUNCH(zero_kernel<uint8_t>, z, st); return permute_cols_launch<uint8_t, true>(p, st);
+            case 2: FMB_EW_LAUNCH(zero_kernel<uint16_t>, z, st); return permute_cols_launch<uint16_t, true>(p, st);
+            case 4: FMB_EW_LAUNCH(zero_kernel<uint32_t>, z, st); return permute_cols_launch<uint32_t, true>(p, st);
+            case 8: FMB_EW_LAUNCH(zero_kernel<uint64_t>, z, st); return permute_cols_launch<uint64_t, true>(p, st);
+            case 16: FMB_EW_LAUNCH(zero_kernel<double2>, z, st); return permute_cols_launch<double2, true>(p, st);
+            default: set_error("Partial: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
+        }
+    }
     switch (dtype_size(dtype)) {
         case 1: FMB_EW_LAUNCH(zero_kernel<uint8_t>, z, st); FMB_EW_LAUNCH(scatter_kernel<uint8_t>, p, st); break;
         case 2: FMB_EW_LAUNCH(zero_kernel<uint16_t>, z, st); FMB_EW_LAUNCH(scatter_kernel<uint16_t>, p, st); break;
