@@ -61,6 +61,8 @@ int diag_apply(const void *d_dev, int dt_d, int64_t n, int conj_d, const void *x
                int64_t ycs, int64_t M, int dt_x, int dt_out, cudaStream_t st);
 int gather_apply(const void *idx_dev, int64_t nsel, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs,
                  int64_t M, int dtype, cudaStream_t st);
+int scatter_inverse_apply(const void *inv_dev, int64_t ntotal, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
+                          int64_t ycs, int64_t M, int dtype, cudaStream_t st);
 int scatter_apply(const void *idx_dev, int64_t nsel, int64_t ntotal, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
                   int64_t ycs, int64_t M, int dtype, cudaStream_t st);
 int conj_apply(const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t n, int64_t M, int dtype, cudaStream_t st);
@@ -236,6 +238,7 @@ struct DiagPlan : PlanBase {
 
 struct PartialPlan : PlanBase {
     DevArray idx;
+    DevArray inv;            // inverse index (ntotal entries, -1 = row not selected), absent for very sparse selections
     int64_t nsel = 0, ntotal = 0;
     int info(fmb_plan_info *o) const override {
         memset(o, 0, sizeof(*o));
@@ -246,6 +249,7 @@ struct PartialPlan : PlanBase {
               int dt_out, void *, int64_t, cudaStream_t st) const override {
         if (dt_in != dt_out) { set_error("Partial: gather/scatter does not convert dtypes"); return FMB_ERR_TYPE; }
         if (direction == FMB_FORWARD) return gather_apply(idx.p, nsel, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);
+        if (inv.p) return scatter_inverse_apply(inv.p, ntotal, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);
         return scatter_apply(idx.p, nsel, ntotal, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);
     }
 };
@@ -369,6 +373,15 @@ int fmb_partial_plan_create(fmb_plan **out, const int64_t *idx_host, int64_t num
     std::unique_ptr<PartialPlan> p(new PartialPlan());
     p->kind = FMB_KIND_PARTIAL; p->num_rows = num_sel; p->num_cols = num_total; p->nsel = num_sel; p->ntotal = num_total;
     if ((rc = p->idx.upload(idx_host, (size_t)num_sel * sizeof(int64_t)))) return rc;
+    // The backward direction (y = 0; y[idx[r]] = x[r]) runs as a gather through the inverse index: no zero-fill pass,
+    // coalesced stores, and a repeated index resolves like numpy's assignment (the last occurrence wins) instead of
+    // racing.  Skipped when the table would dwarf the selection (a few rows out of a huge matrix).
+    static const long inv_on = getenv("FMB_PARTIAL_INVERSE") ? atol(getenv("FMB_PARTIAL_INVERSE")) : 1;
+    if (inv_on && num_sel > 0 && (num_total <= (int64_t)(32 << 20) || num_sel * 8 >= num_total)) {
+        std::vector<int64_t> inv((size_t)num_total, (int64_t)-1);
+        for (int64_t i = 0; i < num_sel; ++i) inv[(size_t)idx_host[i]] = i;
+        if ((rc = p->inv.upload(inv.data(), (size_t)num_total * sizeof(int64_t)))) return rc;
+    }
     *out = reinterpret_cast<fmb_plan *>(static_cast<PlanBase *>(p.release()));
     return FMB_OK;
     FMB_GUARD_END

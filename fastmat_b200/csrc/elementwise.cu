@@ -87,6 +87,20 @@ template <typename B> __global__ void __launch_bounds__(256) gather_kernel(const
     }
 }
 
+template <typename B> __global__ void __launch_bounds__(256) gather_masked_kernel(const __grid_constant__ EwParams p) {
+    // y[r, c] = idx[r] >= 0 ? x[idx[r], c] : 0, r < n   (a scatter expressed through the inverse index)
+    const long long total = p.n * p.M;
+    const long long *idx = (const long long *)p.d;
+    B z;
+    memset(&z, 0, sizeof(B));
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        long long r, c;
+        ew_decode(p, e, r, c);
+        const long long i = __ldg(idx + r);
+        ((B *)p.y)[r * p.yrs + c * p.ycs] = i >= 0 ? ((const B *)p.x)[i * p.xrs + c * p.xcs] : z;
+    }
+}
+
 template <typename B> __global__ void __launch_bounds__(256) scatter_kernel(const __grid_constant__ EwParams p) {
     // y[idx[r], c] = x[r, c], r < n   (y zero-filled beforehand)
     const long long total = p.n * p.M;
@@ -179,13 +193,16 @@ template <typename B, bool SCATTER, int CB> __global__ void __launch_bounds__(25
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.n) return;
     const long long i = __ldg((const long long *)p.d + r);
-    const B *src = (const B *)p.x + (SCATTER ? r : i) * p.xrs;
+    const bool hole = !SCATTER && i < 0;              // inverse index of a scatter: rows nothing is written to are zero
+    const B *src = (const B *)p.x + (SCATTER ? r : (hole ? 0 : i)) * p.xrs;
     B *dst = (B *)p.y + (SCATTER ? i : r) * p.yrs;
     for (long long c0 = (long long)blockIdx.y * CB; c0 < p.M; c0 += (long long)gridDim.y * CB) {
         B v[CB];
 #pragma unroll
-        for (int c = 0; c < CB; ++c)
-            if (c0 + c < p.M) v[c] = src[(c0 + c) * p.xcs];
+        for (int c = 0; c < CB; ++c) {
+            if (hole) memset(&v[c], 0, sizeof(B));
+            else if (c0 + c < p.M) v[c] = src[(c0 + c) * p.xcs];
+        }
 #pragma unroll
         for (int c = 0; c < CB; ++c)
             if (c0 + c < p.M) dst[(c0 + c) * p.ycs] = v[c];
@@ -232,6 +249,34 @@ int gather_apply(const void *idx_dev, int64_t nsel, const void *x, int64_t xrs, 
         case 4: FMB_EW_LAUNCH(gather_kernel<uint32_t>, p, st); break;
         case 8: FMB_EW_LAUNCH(gather_kernel<uint64_t>, p, st); break;
         case 16: FMB_EW_LAUNCH(gather_kernel<double2>, p, st); break;
+        default: set_error("Partial: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
+    }
+    return FMB_OK;
+}
+
+// Scatter through the inverse index (inv[i] = the row of x that lands in row i of y, -1 for none): coalesced stores and
+// no separate zero-fill pass; the random side of the copy is a load (measured on B200, LFSRCirculant order 20, 1024
+// float32 columns: zero + scatter 9.1 ms, this 4.9 ms).
+int scatter_inverse_apply(const void *inv_dev, int64_t ntotal, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
+                          int64_t ycs, int64_t M, int dtype, cudaStream_t st) {
+    EwParams p = ew_params(ntotal, M, x, xrs, xcs, y, yrs, ycs);
+    p.d = inv_dev;
+    if (ew_tiled(p)) {
+        switch (dtype_size(dtype)) {
+            case 1: return permute_cols_launch<uint8_t, false>(p, st);
+            case 2: return permute_cols_launch<uint16_t, false>(p, st);
+            case 4: return permute_cols_launch<uint32_t, false>(p, st);
+            case 8: return permute_cols_launch<uint64_t, false>(p, st);
+            case 16: return permute_cols_launch<double2, false>(p, st);
+            default: set_error("Partial: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
+        }
+    }
+    switch (dtype_size(dtype)) {
+        case 1: FMB_EW_LAUNCH(gather_masked_kernel<uint8_t>, p, st); break;
+        case 2: FMB_EW_LAUNCH(gather_masked_kernel<uint16_t>, p, st); break;
+        case 4: FMB_EW_LAUNCH(gather_masked_kernel<uint32_t>, p, st); break;
+        case 8: FMB_EW_LAUNCH(gather_masked_kernel<uint64_t>, p, st); break;
+        case 16: FMB_EW_LAUNCH(gather_masked_kernel<double2>, p, st); break;
         default: set_error("Partial: unsupported dtype %d", dtype); return FMB_ERR_TYPE;
     }
     return FMB_OK;

@@ -77,3 +77,19 @@ def test_lfsr_circulant_order20_properties(fm):        # noqa: F811
     for i in (0, 1, 12345, n - 1):
         row = c[(i - torch.arange(n, device='cuda')) % n]
         assert torch.equal(yx[i], (row[:, None] * x).sum(dim=0).to(torch.int32))
+
+
+def test_partial_backward_scatter_holes_and_repeats(fm):        # noqa: F811
+    """The backward of a row selection (y = 0; y[idx[r]] = x[r], fastmat/Partial.pyx:282-294) runs as a gather through
+    the inverse index: rows nothing lands in are zero, a repeated index resolves like numpy (last occurrence wins)."""
+    rng = np.random.default_rng(5)
+    n = 1000
+    for idx in (rng.permutation(n)[:333], np.array([7, 3, 7, 999, 0, 3, 7]), np.arange(n)[::-1].copy()):
+        P = fm.Partial(fm.Eye(n), rows=idx)
+        for dt in ('int8', 'int32', 'float64', 'complex128'):
+            x = rng.integers(-100, 100, size=(idx.size, 5)).astype(dt)
+            ref = np.zeros((n, 5), dtype=dt)
+            ref[idx] = x
+            for lay in ('F', 'C'):
+                assert np.array_equal(host(P.backward(dev(x, lay))), ref), (dt, lay)
+            assert np.array_equal(host(P.backward(dev(x[:, 0]))), ref[:, 0])
