@@ -49,5 +49,5 @@ class BlockDiag(Matrix):
         refs = [m.reference() for m in self._content]
         t = refs[0].dtype
         for r in refs:
-            t = torch.promote_types(t, r.dtype)
+            t = _t.promoteTorch(t, r.dtype)
         return torch.block_diag(*[r.to(t) for r in refs])

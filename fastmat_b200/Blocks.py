@@ -5,6 +5,12 @@ from .Matrix import Matrix, cast, alloc_out, is_row_major
 from .core import types as _t
 
 
+def _add(a, b):
+    """a + b in the numpy / fastmat promotion of the two dtypes (not torch's: int32 + float32 is float64 there)."""
+    t = _t.getTorchType(_t.promoteTypes(a.dtype, b.dtype))
+    return a.to(t) + b.to(t)
+
+
 class Blocks(Matrix):
 
     def __init__(self, arrMatrices, **options):
@@ -48,7 +54,7 @@ class Blocks(Matrix):
             c0 = 0
             for term in row:
                 y = term.forward(x[c0:c0 + term.numCols, :])
-                acc = y if acc is None else acc.to(torch.promote_types(acc.dtype, y.dtype)) + y
+                acc = y if acc is None else _add(acc, y)
                 c0 += term.numCols
             outs.append(acc)
         return self._stack(outs, x)
@@ -60,7 +66,7 @@ class Blocks(Matrix):
             xs = x[r0:r0 + self._rowSize[rr], :]
             for cc, term in enumerate(row):
                 y = term.backward(xs)
-                outs[cc] = y if outs[cc] is None else outs[cc].to(torch.promote_types(outs[cc].dtype, y.dtype)) + y
+                outs[cc] = y if outs[cc] is None else _add(outs[cc], y)
             r0 += self._rowSize[rr]
         return self._stack(outs, x)
 
@@ -82,9 +88,9 @@ class Blocks(Matrix):
             refs = [m.reference() for m in row]
             t = refs[0].dtype
             for r in refs:
-                t = torch.promote_types(t, r.dtype)
+                t = _t.promoteTorch(t, r.dtype)
             rows.append(torch.cat([r.to(t) for r in refs], dim=1))
         t = rows[0].dtype
         for r in rows:
-            t = torch.promote_types(t, r.dtype)
+            t = _t.promoteTorch(t, r.dtype)
         return torch.cat([r.to(t) for r in rows], dim=0)

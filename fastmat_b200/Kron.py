@@ -97,6 +97,6 @@ class Kron(Matrix):
         arr = None
         for f in self._content:
             r = f.reference()
-            arr = r if arr is None else torch.kron(arr.to(torch.promote_types(arr.dtype, r.dtype)),
-                                                   r.to(torch.promote_types(arr.dtype, r.dtype)))
+            arr = r if arr is None else torch.kron(arr.to(_t.promoteTorch(arr.dtype, r.dtype)),
+                                                   r.to(_t.promoteTorch(arr.dtype, r.dtype)))
         return arr

@@ -108,6 +108,22 @@ flags = _Flags()
 
 
 # ------------------------------------------------------------------------------------------- Matrix
+def _dense_matmul(a, x):
+    """a @ x in the numpy / fastmat promotion of the two dtypes (core.types.PROMOTE = np.promote_types, NOT
+    torch.promote_types: int32 / int64 with float32 is float64 in numpy and in the reference, fastmat/core/types.pyx:
+    443-453).  cuBLAS has no integer GEMM: integer products run on the device as int64 multiply-accumulate (exact, wraps
+    like numpy) through a broadcast sum in column chunks."""
+    t = _t.getTorchType(_t.promoteTypes(a.dtype, x.dtype))
+    if t.is_floating_point or t.is_complex:
+        return torch.matmul(a.to(t).resolve_conj(), x.to(t))
+    a64, x64 = a.to(torch.int64), x.to(torch.int64)
+    out = torch.empty((a.shape[0], x.shape[1]), dtype=torch.int64, device=x.device)
+    step = max(1, (1 << 24) // max(1, a.shape[0] * a.shape[1]))
+    for c0 in range(0, x.shape[1], step):
+        out[:, c0:c0 + step] = (a64.unsqueeze(2) * x64[:, c0:c0 + step].unsqueeze(0)).sum(dim=1)
+    return out.to(t)
+
+
 class Matrix(object):
     """Dense matrix wrapper and base class of every operator (fastmat/Matrix.pyx:1469-1570)."""
 
@@ -171,20 +187,11 @@ class Matrix(object):
     # ---- overridable transforms
     def _forward(self, x):
         """Dense fallback of the base class itself: array . x (fastmat/Matrix.pyx:1831-1842) via cuBLAS."""
-        a = self._array
-        t = torch.promote_types(a.dtype, x.dtype)
-        if not (t.is_floating_point or t.is_complex):
-            # integer GEMM is not available in cuBLAS: exact in float64 for the magnitudes int matrices carry
-            return torch.matmul(a.to(torch.float64), x.to(torch.float64)).to(t)
-        return torch.matmul(a.to(t), x.to(t))
+        return _dense_matmul(self._array, x)
 
     def _backward(self, x):
         a = self._array
-        t = torch.promote_types(a.dtype, x.dtype)
-        ah = a.conj().t() if a.is_complex() else a.t()
-        if not (t.is_floating_point or t.is_complex):
-            return torch.matmul(ah.to(torch.float64), x.to(torch.float64)).to(t)
-        return torch.matmul(ah.to(t).resolve_conj(), x.to(t))
+        return _dense_matmul(a.conj().t() if a.is_complex() else a.t(), x)
 
     # ---- input preparation (fastmat/Matrix.pyx:1737-1817)
     def _prepare(self, x, required):

@@ -11,22 +11,38 @@ from .Matrix import Matrix, cast
 from .core import types as _t
 
 
+# Python scalars are *weakly* typed, as in numpy >= 2 (NEP 50): their value never decides the operator's dtype.  A python
+# int / float / complex only lifts the KIND of the matrix factors' common type (integer -> int64 / float64 / complex128,
+# the reference's np.array(scalar).dtype; real floating -> the complex type of the same precision) and never its
+# precision, so M * 0.5, M * 0.1, M / 2 and M / 3 all have the dtype class of M, and a single-precision operator stays
+# single.  numpy scalars keep their own dtype (reference: fastmat/Product.pyx:108-114).
+_WEAK_INT, _WEAK_FLOAT, _WEAK_COMPLEX = 1, 2, 3
+
+
 def _scalar_type(f):
-    """Smallest fastmat type holding a python / numpy scalar (numpy scalars keep their own dtype)."""
+    """(fastmat type or None, weak kind or 0) of a scalar factor."""
     if isinstance(f, np.generic):
-        return _t.getFusedType(f.dtype)
-    if isinstance(f, bool):
-        return _t.TYPE_INT8
-    if isinstance(f, int):
-        for t in (np.int8, np.int16, np.int32, np.int64):
-            if np.iinfo(t).min <= f <= np.iinfo(t).max:
-                return _t.getFusedType(t)
-        raise TypeError("Product: integer scalar out of range.")
+        return _t.getFusedType(f.dtype), 0
+    if isinstance(f, (bool, int)):
+        if not (np.iinfo(np.int64).min <= int(f) <= np.iinfo(np.int64).max):
+            raise TypeError("Product: integer scalar out of range.")
+        return None, _WEAK_INT
     if isinstance(f, float):
-        return _t.TYPE_FLOAT32 if float(np.float32(f)) == f else _t.TYPE_FLOAT64
+        return None, _WEAK_FLOAT
     if isinstance(f, complex):
-        return _t.TYPE_COMPLEX64 if complex(np.complex64(f)) == f else _t.TYPE_COMPLEX128
+        return None, _WEAK_COMPLEX
     raise TypeError("Product: Term is neither scalar nor Matrix.")
+
+
+def _apply_weak(ft, weak):
+    """Lift the matrix factors' common type `ft` by the strongest weak python scalar kind seen."""
+    if weak == 0:
+        return ft
+    if _t.isInteger(ft):
+        return {_WEAK_INT: _t.TYPE_INT64, _WEAK_FLOAT: _t.TYPE_FLOAT64, _WEAK_COMPLEX: _t.TYPE_COMPLEX128}[weak]
+    if weak == _WEAK_COMPLEX and not _t.isComplex(ft):
+        return _t.TYPE_COMPLEX64 if ft == _t.TYPE_FLOAT32 else _t.TYPE_COMPLEX128
+    return ft
 
 
 class Product(Matrix):
@@ -36,6 +52,7 @@ class Product(Matrix):
         scalar = [1]
         factors = []
         ft = [_t.TYPE_INT8]
+        weak = [0]
 
         def add(items):
             for f in items:
@@ -54,12 +71,15 @@ class Product(Matrix):
                 elif np.isscalar(f):
                     if f != 1:
                         scalar[0] = scalar[0] * f
-                    ft[0] = _t.promoteTypes(ft[0], _scalar_type(f))
+                    st, wk = _scalar_type(f)
+                    if st is not None:
+                        ft[0] = _t.promoteTypes(ft[0], st)
+                    weak[0] = max(weak[0], wk)
                 else:
                     raise TypeError("Product: Term is neither scalar nor Matrix.")
 
         add(matrices)
-        dtype = ft[0]
+        dtype = _apply_weak(ft[0], weak[0])
         expansion = options.get('typeExpansion', _t.safeTypeExpansion(dtype))
         if expansion is not None:
             dtype = _t.promoteTypes(dtype, expansion)
@@ -139,7 +159,7 @@ class Product(Matrix):
             if arr is None:
                 arr = r
             else:
-                t = torch.promote_types(arr.dtype, r.dtype)
+                t = _t.promoteTorch(arr.dtype, r.dtype)
                 arr = arr.to(t) @ r.to(t)
         if self._scalar != 1:
             arr = arr * (complex(self._scalar) if np.iscomplexobj(self._scalar) else float(self._scalar))

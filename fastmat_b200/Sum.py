@@ -51,5 +51,5 @@ class Sum(Matrix):
         arr = None
         for m in self._content:
             r = m.reference()
-            arr = r if arr is None else arr.to(torch.promote_types(arr.dtype, r.dtype)) + r
+            arr = r if arr is None else arr.to(_t.promoteTorch(arr.dtype, r.dtype)) + r
         return arr

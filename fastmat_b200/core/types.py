@@ -90,3 +90,9 @@ def getTypeEps(obj):
     if t <= TYPE_INT64:
         return 0.0
     return float(np.finfo(_NUMPY[t]).eps)
+
+
+def promoteTorch(a, b):
+    """torch dtype of the numpy / fastmat promotion of two torch (or numpy) dtypes - use this, never
+    torch.promote_types (which differs from numpy: int32 / int64 with float32 gives float32 there)."""
+    return getTorchType(promoteTypes(a, b))

@@ -448,3 +448,9 @@ int fmb_ista_step(const void *x, const void *grad, void *step_out, void *x_out, 
 int64_t fmb_launch_count(void) { return g_launches.load(); }
 
 }  // extern "C"
+
+#ifdef V32_TIMING
+// experiment builds only (-DV32_TIMING): print the phase timings collected by the instrumented kernels
+namespace fmb { std::vector<void (*)()> &debug_dumpers() { static std::vector<void (*)()> v; return v; } }
+extern "C" void fmb_debug_dump(void) { for (auto f : fmb::debug_dumpers()) f(); }
+#endif

@@ -122,9 +122,11 @@ struct PipeScope {
     int ns = 1;
     cudaStream_t caller = nullptr;
     void *pool_ = nullptr;              // the device's stream pool (fft_engine.cu)
+    bool open = false;                  // begin() forked the caller's stream and end() has not joined it yet
     int begin(int ns_, cudaStream_t st);
     cudaStream_t stream(int64_t k) const;
     int end();
+    ~PipeScope() { if (open) end(); }   // error returns inside a slab loop still join the internal streams
 };
 
 // ---- planner (planner.cpp): fastmat/core/cmath.pyx:35-214

@@ -5,7 +5,6 @@
 #include <cmath>
 
 #include "fft_fast.cuh"
-#include "fft_fused.cuh"
 #include "fft_v32.cuh"
 #include "fft_v32p.cuh"
 #include "fft_pass.cuh"
@@ -275,7 +274,6 @@ int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
         int cols, ns;
         slab_plan(M, csize, true, cols, ns);
         int64_t w = std::max(generic, (int64_t)cols * ns * L * (int64_t)csize);
-        if (kron_a == 0) w = std::max(w, fused_workspace_bytes(M, csize));
         if (csize == sizeof(float2)) w = std::max(w, v32p_workspace_bytes(M));
         return w;
     }
@@ -318,11 +316,13 @@ int PipeScope::begin(int ns_, cudaStream_t st) {
     if (rc) return rc;
     FMB_CUDA_OK(cudaEventRecord(pool.fork, st));
     for (int i = 0; i < ns; ++i) FMB_CUDA_OK(cudaStreamWaitEvent(pool.s[i], pool.fork, 0));
+    open = true;
     return FMB_OK;
 }
 cudaStream_t PipeScope::stream(int64_t k) const { return ns > 1 ? static_cast<StreamPool *>(pool_)->s[k % ns] : caller; }
 int PipeScope::end() {
-    if (ns == 1) return FMB_OK;
+    if (ns == 1 || !open) return FMB_OK;
+    open = false;
     StreamPool &pool = *static_cast<StreamPool *>(pool_);
     for (int i = 0; i < ns; ++i) {
         FMB_CUDA_OK(cudaEventRecord(pool.join[i], pool.s[i]));
@@ -558,15 +558,19 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
 }
 
 // ------------------------------------------------------------------------------------------- V32 path (fft_v32.cuh)
-int launch_v32_a(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
-int launch_v32_b(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
-int launch_v32_m(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
-int launch_v32_c(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
-static int launch_v32(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
-    int rc = launch_v32_a(opt, a, tiles, st);
-    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_b(opt, a, tiles, st);
-    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_m(opt, a, tiles, st);
-    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_c(opt, a, tiles, st);
+int launch_v32_a(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
+int launch_v32_b(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
+int launch_v32_m(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
+int launch_v32_c(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
+// tile / occupancy instantiation (fft_v32.cuh: launch_v32_variant): FMB_V32_OCC for the strided passes, FMB_V32_MSHAPE for
+// the middle pass of a convolution
+static int launch_v32(unsigned opt, const FastArgs<float2> &a, unsigned lines, cudaStream_t st) {
+    static const long occ = env_long("FMB_V32_OCC", 0), mshape = env_long("FMB_V32_MSHAPE", 0);
+    const int shape = (int)((opt & FO_TWO_FFTS) ? mshape : occ);
+    int rc = launch_v32_a(opt, a, lines, shape, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_b(opt, a, lines, shape, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_m(opt, a, lines, shape, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_c(opt, a, lines, shape, st);
     if (rc == FMB_ERR_NOTIMPL) set_error("V32 path: unknown pass variant %u", opt);
     return rc;
 }
@@ -592,6 +596,9 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
     const C *pre_d = (const C *)(bwd ? d.post.p : d.pre.p);
     const C *post_d = (const C *)(bwd ? d.pre.p : d.post.p);
     const int R1 = 1024, R2 = 1024, l1 = 10, l2 = 10;
+    // the four-step twiddle between the inverse transform's two passes rides on the LAST pass's loads (FMB_V32_TWM=1: on
+    // the middle pass's stores, as in round 1): the middle pass is the FP32-bound one, the last pass waits for its loads
+    static const bool tw_in_c = env_long("FMB_V32_TWM", 0) == 0;
     int slab_i, ns;
     slab_plan(M, sizeof(C), true, slab_i, ns);
     const int64_t slab = slab_i;
@@ -606,7 +613,7 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
             st = pipe.stream(slab_idx);
             ws = (char *)ws_base + (size_t)(slab_idx % ns) * (size_t)slab * (size_t)L * sizeof(C);
         }
-        const unsigned tiles = (unsigned)((nc * 1024) >> V32_LOGT);
+        const unsigned tiles = (unsigned)(nc * 1024);          // lines; the launcher divides by its tile width
         FastArgs<C> base;
         memset(&base, 0, sizeof(base));
         base.ncols = (int)nc;
@@ -657,7 +664,7 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
                 a.out = (C *)ws; a.out_cs = L; a.out_ks = 1; a.out_is = R2;
                 a.mid = (const C *)d.mid.p; a.mid_is = R2;
                 a.tw = (const C *)d.twV[1].p; a.twS = (const C *)d.twS32[1].p;
-                if ((rc = launch_v32(bwd ? V32_BMC : V32_BM, a, tiles, st))) return rc;
+                if ((rc = launch_v32(tw_in_c ? (bwd ? V32_BMC_N : V32_BM_N) : (bwd ? V32_BMC : V32_BM), a, tiles, st))) return rc;
             }
             {   // ---- pass C: length R1 over k1 (stride R2 in ws), lines m2; conj, post-multiply, truncate; out y[m1*R2 + m2]
                 FastArgs<C> a = base;
@@ -665,8 +672,9 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
                 a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R2; a.out_is = 1;
                 a.out_n = (int)rows_out; a.out_lk = R2; a.out_li = 1;
                 a.post = post_d;
-                a.tw = (const C *)d.twV[0].p;
+                a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[1].p;
                 unsigned opt = post_d ? (bwd ? V32_C_MPC : V32_C_MP) : (rows_out == L ? V32_C_N : V32_C_M);
+                if (tw_in_c) opt |= V32_C_TW;
                 if ((rc = launch_v32(opt, a, tiles, st))) return rc;
             }
         }
@@ -850,149 +858,6 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
 #endif
 }
 
-// ------------------------------------------------------------------------------------------- fused persistent path
-int launch_fused_f32_8_8(int variant, const FusedArgs<float2> &g, cudaStream_t st);
-int launch_fused_f32_8_9(int variant, const FusedArgs<float2> &g, cudaStream_t st);
-int launch_fused_f32_9_9(int variant, const FusedArgs<float2> &g, cudaStream_t st);
-int launch_fused_f32_9_10(int variant, const FusedArgs<float2> &g, cudaStream_t st);
-int launch_fused_f32_10_10(int variant, const FusedArgs<float2> &g, cudaStream_t st);
-int launch_fused_f32_10_11(int variant, const FusedArgs<float2> &g, cudaStream_t st);
-int launch_fused_f32_11_11(int variant, const FusedArgs<float2> &g, cudaStream_t st);
-int launch_fused_f64_8_8(int variant, const FusedArgs<double2> &g, cudaStream_t st);
-
-static int fused_launch(int l1, int l2, int variant, const FusedArgs<float2> &g, cudaStream_t st) {
-    switch (l1 * 16 + l2) {
-        case 8 * 16 + 8: return launch_fused_f32_8_8(variant, g, st);
-        case 8 * 16 + 9: return launch_fused_f32_8_9(variant, g, st);
-        case 9 * 16 + 9: return launch_fused_f32_9_9(variant, g, st);
-        case 9 * 16 + 10: return launch_fused_f32_9_10(variant, g, st);
-        case 10 * 16 + 10: return launch_fused_f32_10_10(variant, g, st);
-        case 10 * 16 + 11: return launch_fused_f32_10_11(variant, g, st);
-        case 11 * 16 + 11: return launch_fused_f32_11_11(variant, g, st);
-        default: set_error("fused path: unsupported pass lengths"); return FMB_ERR_NOTIMPL;
-    }
-}
-static int fused_launch(int l1, int l2, int variant, const FusedArgs<double2> &g, cudaStream_t st) {
-    if (l1 == 8 && l2 == 8) return launch_fused_f64_8_8(variant, g, st);
-    set_error("fused path: unsupported pass lengths");
-    return FMB_ERR_NOTIMPL;
-}
-static bool fused_has(const float2 *, int l1, int l2) { return l1 >= 8 && l2 <= 11 && (l2 == l1 || l2 == l1 + 1); }
-static bool fused_has(const double2 *, int l1, int l2) { return l1 == 8 && l2 == 8; }
-
-struct FusedGeom { int slab_cols, delay, npass, nslot; int64_t nslabs, counter_bytes, ring_bytes; };
-static FusedGeom fused_geom(int64_t M, int64_t L, size_t csize, bool two) {
-    static const long slab_env = env_long("FMB_FUSED_SLAB", 1), delay_env = env_long("FMB_FUSED_DELAY", 2);
-    FusedGeom f;
-    f.slab_cols = (int)std::max<long>(1, slab_env);
-    f.delay = (int)std::max<long>(1, delay_env);
-    f.npass = two ? 3 : 2;
-    f.nslot = (f.npass - 1) * f.delay + 2;
-    f.nslabs = (M + f.slab_cols - 1) / f.slab_cols;
-    f.counter_bytes = ((int64_t)4 * (4 + 3 * f.nslabs) + 255) / 256 * 256;
-    f.ring_bytes = (int64_t)f.nslot * f.slab_cols * L * (int64_t)csize;
-    return f;
-}
-
-int64_t ConvEngine::fused_workspace_bytes(int64_t M, size_t csize) const {
-    FusedGeom f = fused_geom(M, L, csize, two_ffts);
-    return f.counter_bytes + f.ring_bytes;
-}
-
-template <typename C> bool ConvEngine::fused_ok() const {
-#ifdef FMB_EMULATE
-    return false;
-#else
-    // The fused persistent pipeline (fft_fused.cuh) keeps HBM traffic at the algorithmic minimum but, as measured on
-    // B200 in round 1, its per-tile scheduling overhead makes it slower than one launch per pass (DESIGN.md "status of
-    // the fused kernel"); it is therefore opt-in until that overhead is gone.
-    static const long on = env_long("FMB_FUSED", 0);
-    if (!on || kron_a > 0) return false;
-    return fused_has((const C *)nullptr, ilog2_host(shape.g[0].R), ilog2_host(shape.g[1].R));
-#endif
-}
-
-template <typename C>
-int ConvEngine::run_fused(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws,
-                          int64_t ws_bytes, cudaStream_t st) const {
-#ifdef FMB_EMULATE
-    return FMB_ERR_NOTIMPL;
-#else
-    const bool bwd = direction == FMB_BACKWARD;
-    const int64_t rows_in = bwd ? n_out : n_in, rows_out = bwd ? n_in : n_out;
-    const C *pre_d = (const C *)(bwd ? d.post.p : d.pre.p);
-    const C *post_d = (const C *)(bwd ? d.pre.p : d.post.p);
-    const int R1 = shape.g[0].R, R2 = shape.g[1].R;
-    const int l1 = ilog2_host(R1), l2 = ilog2_host(R2);
-    const int lt1 = 13 - l1 - (sizeof(C) == 16 ? 1 : 0), lt2 = 13 - l2 - (sizeof(C) == 16 ? 1 : 0);
-    const FusedGeom f = fused_geom(M, L, sizeof(C), two_ffts);
-    if (ws == nullptr || ws_bytes < f.counter_bytes + f.ring_bytes) {
-        set_error("workspace too small: need %lld bytes", (long long)(f.counter_bytes + f.ring_bytes));
-        return FMB_ERR_WORKSPACE;
-    }
-    FMB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)f.counter_bytes, st));
-    C *ring = (C *)((char *)ws + f.counter_bytes);
-    FusedArgs<C> g;
-    memset(&g, 0, sizeof(g));
-    g.npass = f.npass; g.ncols = (int)M; g.slab_cols = f.slab_cols; g.nslabs = (int)f.nslabs;
-    g.delay = f.delay; g.nslot = f.nslot;
-    g.slot_stride = (long long)f.slab_cols * L;
-    g.x_slab_stride = (long long)f.slab_cols * xcs;
-    g.y_slab_stride = (long long)f.slab_cols * ycs;
-    g.work_counter = (unsigned *)ws;
-    g.done = (unsigned *)ws + 4;
-    FastArgs<C> base;
-    memset(&base, 0, sizeof(base));
-    base.ncols = f.slab_cols;
-    base.twL = (const C *)d.twL.p; base.twH = (const C *)d.twH.p; base.tw_shift = d.tw_shift;
-    base.tw_mask = (unsigned)(((int64_t)1 << d.tw_shift) - 1);
-    {   // pass A
-        FastArgs<C> a = base;
-        a.in = (const C *)x; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
-        a.out = ring; a.out_cs = L; a.out_ks = 1; a.out_is = R1;
-        a.I = R2; a.logI = l2;
-        a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
-        a.tw = (const C *)d.twF[0].p; a.twS = (const C *)d.twS[0].p;
-        a.pre = pre_d;
-        g.pass[0] = a;
-        g.tiles[0] = (unsigned)(((int64_t)f.slab_cols * R2) >> lt1);
-    }
-    int variant;
-    if (!two_ffts) {
-        FastArgs<C> a = base;
-        a.in = ring; a.in_cs = L; a.in_fs = R1; a.in_is = 1;
-        a.out = (C *)y; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
-        a.I = R1; a.logI = l1;
-        a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
-        a.tw = (const C *)d.twF[1].p;
-        g.pass[1] = a;
-        g.tiles[1] = (unsigned)(((int64_t)f.slab_cols * R1) >> lt2);
-        variant = bwd ? 1 : 0;
-    } else {
-        FastArgs<C> a = base;
-        a.in = ring; a.in_cs = L; a.in_fs = R1; a.in_is = 1;
-        a.out = ring; a.out_cs = L; a.out_ks = R1; a.out_is = 1;
-        a.I = R1; a.logI = l1;
-        a.mid = (const C *)d.mid.p; a.mid_is = R2;
-        a.tw = (const C *)d.twF[1].p; a.twS = (const C *)d.twS[1].p;
-        g.pass[1] = a;
-        g.tiles[1] = (unsigned)(((int64_t)f.slab_cols * R1) >> lt2);
-        FastArgs<C> c = base;
-        c.in = ring; c.in_cs = L; c.in_fs = 1; c.in_is = R1;
-        c.out = (C *)y; c.out_cs = ycs; c.out_ks = R2; c.out_is = 1;
-        c.I = R2; c.logI = l2;
-        c.out_n = (int)rows_out; c.out_lk = R2; c.out_li = 1;
-        c.post = post_d;
-        c.tw = (const C *)d.twF[0].p;
-        g.pass[2] = c;
-        g.tiles[2] = (unsigned)(((int64_t)f.slab_cols * R2) >> lt1);
-        variant = pre_d ? (bwd ? 5 : 4) : (bwd ? 3 : 2);
-    }
-    g.items_per_step = g.tiles[0] + g.tiles[1] + g.tiles[2];
-    g.total_items = (unsigned)((f.nslabs + (int64_t)(f.npass - 1) * f.delay) * g.items_per_step);
-    return fused_launch(l1, l2, variant, g, st);
-#endif
-}
 
 template <typename C>
 int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t xcs, bool in_real, void *y, int64_t yrs,
@@ -1030,7 +895,6 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
             set_error("workspace too small: need %lld bytes", (long long)workspace_bytes(M, sizeof(C)));
             return FMB_ERR_WORKSPACE;
         }
-        if (fused_ok<C>()) return run_fused<C>(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
         if (v32_ok(sizeof(C)) && v32p_ok(direction, x, xcs, y, ycs)) return run_v32p(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
         if (v32_ok(sizeof(C))) return run_v32(d, direction, x, xcs, y, ycs, M, ws, st);
         return run_fast<C>(d, direction, x, xcs, y, ycs, M, ws, st);

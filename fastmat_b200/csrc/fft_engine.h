@@ -69,11 +69,6 @@ struct ConvEngine {
     int run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes,
                  cudaStream_t st) const;
     int64_t v32p_workspace_bytes(int64_t M) const;
-    template <typename C> bool fused_ok() const;
-    template <typename C>
-    int run_fused(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes,
-                  cudaStream_t st) const;
-    int64_t fused_workspace_bytes(int64_t M, size_t csize) const;
     template <typename C>
     int run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t xcs, bool in_real, void *y, int64_t yrs, int64_t ycs,
               int64_t M, void *ws, int64_t ws_bytes, cudaStream_t st) const;

@@ -76,6 +76,7 @@ enum : unsigned {
     FO_PRE = 512u, FO_PRE_CONJ = 1024u,
     FO_POST = 2048u, FO_POST_CONJ = 4096u,
     FO_IN_CG = 8192u,      // the input was written by other SMs in this launch (read through L2 only)
+    FO_IN_TWIDDLE = 16384u,  // V32 passes: multiply the INPUT by W_N^{i f} (the four-step twiddle moved out of the previous pass)
 };
 
 template <typename C> __device__ __forceinline__ C ld_cg(const C *p) { return __ldcg(p); }

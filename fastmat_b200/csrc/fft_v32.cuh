@@ -13,13 +13,14 @@
 // Same argument block and option bits as the fast path (FastArgs / FO_*); 256 threads, 8 lines per tile, <= 128
 // registers, 2 CTAs per SM.  complex64 only (complex128 stays on the 16-value path: 32 double2 values do not fit).
 #pragma once
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 #include "fft_fast.cuh"
 
 namespace fmb {
 
-#ifndef V32_MINB
-#define V32_MINB 2
-#endif
 constexpr int V32_LOGT = 3, V32_T = 1 << V32_LOGT, V32_NT = 256;
 constexpr int V32_RS = 1058;                   // line stride: 1024 + one pad per 32, == 2 (mod 16) (see fft_fast.cuh)
 constexpr size_t V32_SMEM = (size_t)V32_T * V32_RS * sizeof(float2);
@@ -97,8 +98,8 @@ template <typename C, typename PrepOdd> __device__ __forceinline__ void dft32_la
     dft32_combine<C, 0>(v, e, o);
 }
 
-template <bool ORDER_T> __device__ __forceinline__ void v32_pos(int tid, int &jb, int &t) {
-    if (ORDER_T) { t = tid & (V32_T - 1); jb = tid >> V32_LOGT; }
+template <bool ORDER_T, int LOGT = 3> __device__ __forceinline__ void v32_pos(int tid, int &jb, int &t) {
+    if (ORDER_T) { t = tid & ((1 << LOGT) - 1); jb = tid >> LOGT; }
     else { jb = tid & 31; t = tid >> 5; }
 }
 
@@ -108,25 +109,77 @@ template <bool WARP> __device__ __forceinline__ void v32_sync() {
     else __syncthreads();
 }
 
-template <unsigned OPT>
-__global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid_constant__ FastArgs<float2> a) {
+// Four-step twiddle W_L^{i (jb + 32 q)}, q = 0..31, of line i as four interleaved chains: c[b] = W^{i jb} s^b (b < 4) with
+// s = W_L^{32 i}, each advanced by s4 = s^4 after use (value q is c[q & 3] at the time it is used).
+struct V32Chain { float2 c[4], s4; };
+__device__ __forceinline__ V32Chain v32_chain_init(const FastArgs<float2> &a, unsigned i, int jb) {
     typedef float2 C;
+    V32Chain h;
+    const unsigned e = i * (unsigned)jb;
+    h.c[0] = cmul(__ldg(a.twL + (e & a.tw_mask)), __ldg(a.twH + (e >> a.tw_shift)));
+    const C s1 = __ldg(a.twS + i);
+    const C s2 = cmul(s1, s1);
+    h.c[1] = cmul(h.c[0], s1);
+    h.c[2] = cmul(h.c[0], s2);
+    h.c[3] = cmul(h.c[1], s2);
+    h.s4 = cmul(s2, s2);
+    return h;
+}
+
+#ifdef V32_TIMING
+std::vector<void (*)()> &debug_dumpers();        // capi.cu; run by fmb_debug_dump()
+// Phase timing (experiment builds only, -DV32_TIMING): lane 0 of every warp of every 16th CTA records the SM clock at the
+// phase boundaries; the clock read is predicated on a value the phase produced, so it cannot be scheduled before it.
+constexpr int V32_TREC = 1 << 16, V32_TFIELDS = 8;
+__device__ __forceinline__ unsigned long long v32_clock_after(float dep) {
+    unsigned long long t;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.neu.f32 p, %1, %1;\n\t@!p mov.u64 %0, %%clock64;\n\t@p mov.u64 %0, 0;\n\t}" : "=l"(t) : "f"(dep) : "memory");
+    return t;
+}
+#define V32_T_DECL unsigned long long tph[V32_TFIELDS] = {}; int tn = 0; const bool trec = tbuf != nullptr && (blockIdx.x & 15) == 0 && (threadIdx.x & 31) == 0;
+#define V32_T_MARK(dep) do { if (trec) tph[tn] = v32_clock_after(dep); ++tn; } while (0)
+#else
+#define V32_T_DECL
+#define V32_T_MARK(dep) do { } while (0)
+#endif
+
+// Geometry is fixed (L = 1024 x 1024, everything but the column stride): line-fastest sides address element (f, i) of a
+// column at f * 1024 + i, row-fastest sides at i * 1024 + f, so that a thread's 32 loads / stores are ONE base register
+// plus immediates (the run-time strides of the general FastArgs cost ~6 integer instructions per access: a fifth of the
+// instructions of the strided passes).  launch_v32_variant() checks that the arguments describe exactly this geometry.
+template <unsigned OPT, int LOGT, int MINB>
+__global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid_constant__ FastArgs<float2> a
+#ifdef V32_TIMING
+                                                                      , unsigned long long *tbuf, unsigned *tcount
+#endif
+) {
+    typedef float2 C;
+    V32_T_DECL
     extern __shared__ __align__(16) unsigned char fmb_v32_smem[];
     C *const smem = reinterpret_cast<C *>(fmb_v32_smem);
     constexpr bool LOAD_T = (OPT & FO_LOAD_T) != 0, STORE_T = (OPT & FO_STORE_T) != 0, TWO = (OPT & FO_TWO_FFTS) != 0;
+    static_assert(LOGT == V32_LOGT || (!LOAD_T && !STORE_T), "strided sides need the 8-line tile (64-byte segments)");
     const int tid = threadIdx.x;
-    const unsigned line0 = blockIdx.x << V32_LOGT;
-    const unsigned col = line0 >> a.logI;                  // 8 divides I: a tile never straddles two columns
-    const unsigned i0 = line0 & (unsigned)(a.I - 1);
+    const unsigned line0 = blockIdx.x << LOGT;
+    const unsigned col = line0 >> 10;                      // the tile width divides 1024: a tile never straddles two columns
+    const unsigned i0 = line0 & 1023u;
     C v[32];
     int jb, t;
 
+    V32_T_MARK(0.f);
+    // Stage twiddles are read through L1 where they are needed.  Measured alternatives (round 2, profiles/r2_experiments.txt):
+    // copying the 8 KB table into shared memory with cp.async at the start of the CTA shortens the second stage (the L1 is
+    // cold after every launch boundary) but the copy competes with the tile's own loads: +4 % overall; requesting the
+    // store side's chain start values up front costs registers during the load phase: +40 %.
+    const CPair<C> *const tab = reinterpret_cast<const CPair<C> *>(a.tw);
     // ------------------------------------------------------------------ global -> registers, first radix-32 stage
-    v32_pos<LOAD_T>(tid, jb, t);
+    v32_pos<LOAD_T, LOGT>(tid, jb, t);
     {
         const unsigned i = i0 + t;
-        const C *src = a.in + (long long)col * a.in_cs + (long long)i * a.in_is + (long long)jb * a.in_fs;
-        const long long fstep = (long long)32 * a.in_fs;
+        const C *src = a.in + (long long)col * a.in_cs + (LOAD_T ? (int)i + jb * 1024 : (int)i * 1024 + jb);
+        constexpr int fstep = 32 * 1024;
+        V32Chain h;
+        if (OPT & FO_IN_TWIDDLE) h = v32_chain_init(a, i, jb);
         // zero padding: logical row f*in_lf + i*in_li < in_n  <=>  32 m < (number of valid f) - jb, one compare per value
         int flim = 0;
         if (OPT & FO_IN_MASK) {
@@ -155,23 +208,33 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
                     val = (OPT & FO_PRE_CONJ) ? cmulc(val, w) : cmul(val, w);
                 }
             }
+            if (OPT & FO_IN_TWIDDLE) {
+                // the four-step twiddle of the PREVIOUS pass's output, applied here: the chain arithmetic runs while the
+                // loads are in flight, and the (FP32-bound) middle pass of a convolution is relieved of it
+                val = cmul(val, h.c[m & 3]);
+                if (m + 4 < 32) h.c[m & 3] = cmul(h.c[m & 3], h.s4);
+            }
             v[m] = val;
         }
     }
+#ifdef V32_TIMING
+    V32_T_MARK(v[0].x + v[31].y + v[16].x + v[15].y);                   // (most) loads have arrived, input-side multiplies done
+#endif
     dft32(v);
-    {
-        C *sl = smem + t * V32_RS + jb * 33;                            // position k = 32 jb + q at k + (k >> 5)
+    V32_T_MARK(v[0].x + v[31].y);                                       // first butterfly done
+    auto exchange_store = [&](int jb_, int t_) {
+        C *sl = smem + t_ * V32_RS + jb_ * 33;                          // position k = 32 jb + q at k + (k >> 5)
 #pragma unroll
         for (int q = 0; q < 32; ++q) sl[q] = v[q];
-    }
+    };
+    exchange_store(jb, t);
 
-    const CPair<C> *const tab = reinterpret_cast<const CPair<C> *>(a.tw);
     // second radix-32 stage: v[m] <- position jb + 32 m, times W_1024^{jb m}, DFT; leaves X[jb + 32 q] in v[q]
-    auto stage_b = [&](int jb_, int t_, const CPair<C> *tb) {
+    auto stage_b = [&](int jb_, int t_) {
         const C *sl = smem + t_ * V32_RS + jb_;
 #pragma unroll
         for (int m = 0; m < 32; ++m) v[m] = sl[33 * m];
-        const CPair<C> *tp = tb + jb_;
+        const CPair<C> *tp = tab + jb_;
 #pragma unroll
         for (int p2 = 0; p2 < 16; ++p2) {
 #ifdef V32_DEBUG_NOTW                                                   /* timing experiment only */
@@ -188,20 +251,10 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
     // last stage output -> global: four-step twiddle W^{i k}, conj, mask, post-multiply
     auto final_store = [&](int jb_, int t_) {
         const unsigned i = i0 + t_;
-        C *dst = a.out + (long long)col * a.out_cs + (long long)i * a.out_is + (long long)jb_ * a.out_ks;
-        const long long kstep = (long long)32 * a.out_ks;
-        C c[4], s4 = mk<C>(1, 0);
-        if (OPT & FO_TWIDDLE) {
-            // W^{i (jb + 32 q)} = W^{i jb} * (W^{32 i})^q: four interleaved chains c[b] = W^{i jb} s^b, each stepped by s^4
-            const unsigned e = i * (unsigned)jb_;
-            c[0] = cmul(__ldg(a.twL + (e & a.tw_mask)), __ldg(a.twH + (e >> a.tw_shift)));
-            const C s1 = __ldg(a.twS + i);
-            const C s2 = cmul(s1, s1);
-            c[1] = cmul(c[0], s1);
-            c[2] = cmul(c[0], s2);
-            c[3] = cmul(c[1], s2);
-            s4 = cmul(s2, s2);
-        }
+        C *dst = a.out + (long long)col * a.out_cs + (STORE_T ? (int)i + jb_ * 1024 : (int)i * 1024 + jb_);
+        constexpr int kstep = 32 * 1024;
+        V32Chain hst;
+        if (OPT & FO_TWIDDLE) hst = v32_chain_init(a, i, jb_);
         int klim = 0;                                                    // truncation: k*out_lk + i*out_li < out_n
         if (OPT & FO_OUT_MASK) {
             const int room = a.out_n - (int)i * a.out_li;
@@ -211,8 +264,8 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
         for (int q = 0; q < 32; ++q) {
             C val = v[q];
             if (OPT & FO_TWIDDLE) {
-                val = cmul(val, c[q & 3]);
-                if (q + 4 < 32) c[q & 3] = cmul(c[q & 3], s4);
+                val = cmul(val, hst.c[q & 3]);
+                if (q + 4 < 32) hst.c[q & 3] = cmul(hst.c[q & 3], hst.s4);
             }
             if (OPT & FO_OUT_CONJ) val = cconj(val);
             const int k = jb_ + 32 * q;
@@ -234,15 +287,19 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
         }
     };
 
+    constexpr bool WARP_ONLY_1 = TWO ? !LOAD_T : (!LOAD_T && !STORE_T);   // lines stay inside one warp: __syncwarp() suffices
     if constexpr (!TWO) {
-        v32_sync<!LOAD_T && !STORE_T>();
-        v32_pos<STORE_T>(tid, jb, t);
-        stage_b(jb, t, tab);
+        v32_sync<WARP_ONLY_1>();
+        V32_T_MARK(0.f);                                                // exchange stores issued, barrier passed
+        v32_pos<STORE_T, LOGT>(tid, jb, t);
+        stage_b(jb, t);
+        V32_T_MARK(v[0].x + v[31].y);                                   // second stage done
         final_store(jb, t);
+        V32_T_MARK(0.f);                                                // stores issued
     } else {
         // ---- middle pass of a convolution.  Inner stages are row-fastest: lane jb of warp t owns line t.
-        v32_sync<!LOAD_T>();
-        v32_pos<false>(tid, jb, t);
+        v32_sync<WARP_ONLY_1>();
+        v32_pos<false, LOGT>(tid, jb, t);
         // Spectrum values of this thread's outputs k = jb + 32 q (one L2 round trip each): those of the even q are
         // requested now - the registers of v are free between the exchange store and load - and arrive during the second
         // stage; those of the odd q are requested once the even ones are consumed and arrive during the even half of the
@@ -251,7 +308,8 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
         C mh[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r));
-        stage_b(jb, t, tab);
+        stage_b(jb, t);
+        V32_T_MARK(v[0].x + v[31].y);                                   // first transform done
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[2 * r] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r], mh[r]) : cmul(v[2 * r], mh[r]));
 #pragma unroll
@@ -263,16 +321,23 @@ __global__ void __launch_bounds__(V32_NT, V32_MINB) v32_pass_kernel(const __grid
             for (int r = 0; r < 16; ++r)
                 v[2 * r + 1] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r + 1], mh[r]) : cmul(v[2 * r + 1], mh[r]));
         });
-        {
-            C *sl = smem + t * V32_RS + jb * 33;
-#pragma unroll
-            for (int q = 0; q < 32; ++q) sl[q] = v[q];
-        }
+        V32_T_MARK(v[0].x + v[31].y);                                   // spectrum product + first stage of the second transform
+        exchange_store(jb, t);
         v32_sync<!STORE_T>();
-        v32_pos<STORE_T>(tid, jb, t);
-        stage_b(jb, t, tab + 512);            // second copy of the table: identical loads would be merged with the first
-        final_store(jb, t);                   // transform's and all sixteen pairs kept in registers across the pass
+        v32_pos<STORE_T, LOGT>(tid, jb, t);
+        V32_T_MARK(0.f);
+        stage_b(jb, t);                       // (the twiddle loads are volatile asm: not merged with the first transform's)
+        V32_T_MARK(v[0].x + v[31].y);
+        final_store(jb, t);
+        V32_T_MARK(0.f);
     }
+#ifdef V32_TIMING
+    if (trec) {
+        const unsigned r = atomicAdd(tcount, 1u);
+        if (r < (unsigned)V32_TREC)
+            for (int f = 0; f < V32_TFIELDS; ++f) tbuf[(size_t)r * V32_TFIELDS + f] = tph[f];
+    }
+#endif
 }
 
 // ---- pass variants used by the engine (fft_engine.cu: run_v32); the intermediate is [k1][n2] (n2 contiguous)
@@ -287,24 +352,88 @@ constexpr unsigned V32_B_N = FO_STORE_T;                                        
 constexpr unsigned V32_B_NC = V32_B_N | FO_OUT_CONJ;
 constexpr unsigned V32_BM = FO_TWO_FFTS | FO_TWIDDLE;                            // middle pass: contiguous lines, in place
 constexpr unsigned V32_BMC = V32_BM | FO_MID_CONJ;
+constexpr unsigned V32_BM_N = FO_TWO_FFTS;                                       // ... its output twiddle left to the last pass
+constexpr unsigned V32_BMC_N = V32_BM_N | FO_MID_CONJ;
 constexpr unsigned V32_C_M = FO_LOAD_T | FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK; // last pass of a convolution
 constexpr unsigned V32_C_N = FO_LOAD_T | FO_STORE_T | FO_OUT_CONJ;               // ... all rows kept: no store mask
 constexpr unsigned V32_C_MP = V32_C_M | FO_POST;
 constexpr unsigned V32_C_MPC = V32_C_MP | FO_POST_CONJ;
+constexpr unsigned V32_C_TW = FO_IN_TWIDDLE;                                     // or-ed to V32_C_*: four-step twiddle on the loads
 constexpr unsigned V32_K_A = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK;               // Kron: over i1 (stride), natural order out
 constexpr unsigned V32_K_AC = V32_K_A | FO_IN_CONJ;
 constexpr unsigned V32_K_B = FO_OUT_MASK;                                        // Kron: over i2 (contiguous)
 constexpr unsigned V32_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
 
-template <unsigned OPT> int launch_v32_variant(const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
+// `shape` selects the tile / occupancy instantiation: strided passes 0 = 8 lines, 2 CTAs per SM (128 registers), 1 = 8 lines,
+// 3 CTAs per SM (80 registers); the middle pass of a convolution (warp-private lines, no CTA barrier) additionally
+// 2 / 3 / 4 = 4 lines per CTA at 4 / 5 / 6 CTAs per SM (128 / 96 / 80 registers)
+template <unsigned OPT, int LOGT, int MINB> int launch_v32_inst(const FastArgs<float2> &a, unsigned lines, cudaStream_t st) {
+    constexpr bool LOAD_T = (OPT & FO_LOAD_T) != 0, STORE_T = (OPT & FO_STORE_T) != 0;
+    constexpr size_t smem = (size_t)(1 << LOGT) * V32_RS * sizeof(float2);
+    if (a.in_fs != (LOAD_T ? 1024 : 1) || a.in_is != (LOAD_T ? 1 : 1024) || a.out_ks != (STORE_T ? 1024 : 1) ||
+        a.out_is != (STORE_T ? 1 : 1024) || a.I != 1024) {
+        set_error("V32 pass: arguments do not describe the fixed 1024 x 1024 geometry");
+        return FMB_ERR_VALUE;
+    }
     static int attr_done = 0;
     if (!attr_done) {
-        FMB_CUDA_OK(cudaFuncSetAttribute(v32_pass_kernel<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)V32_SMEM));
+        FMB_CUDA_OK(cudaFuncSetAttribute(v32_pass_kernel<OPT, LOGT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        if (const char *cv = getenv("FMB_V32_CARVEOUT"))          // experiments: shared-memory share of the unified L1 (percent)
+            FMB_CUDA_OK(cudaFuncSetAttribute(v32_pass_kernel<OPT, LOGT, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(cv)));
         attr_done = 1;
     }
-    v32_pass_kernel<OPT><<<tiles, V32_NT, V32_SMEM, st>>>(a);
+#ifdef V32_TIMING
+    struct TimingDump {
+        unsigned long long *buf = nullptr; unsigned *cnt = nullptr;
+        void dump() {
+            if (!buf) return;
+            cudaDeviceSynchronize();
+            unsigned n = 0;
+            cudaMemcpy(&n, cnt, 4, cudaMemcpyDeviceToHost);
+            n = n < (unsigned)V32_TREC ? n : (unsigned)V32_TREC;
+            std::vector<unsigned long long> h((size_t)n * V32_TFIELDS);
+            cudaMemcpy(h.data(), buf, h.size() * 8, cudaMemcpyDeviceToHost);
+            double acc[V32_TFIELDS] = {};
+            for (unsigned r = 0; r < n; ++r)
+                for (int f = 1; f < V32_TFIELDS; ++f)
+                    if (h[(size_t)r * V32_TFIELDS + f]) acc[f] += (double)(h[(size_t)r * V32_TFIELDS + f] - h[(size_t)r * V32_TFIELDS + f - 1]);
+            fprintf(stderr, "V32_TIMING opt %u logt %d minb %d: %u warp records, mean cycles per phase:", OPT, LOGT, MINB, n);
+            for (int f = 1; f < V32_TFIELDS; ++f) fprintf(stderr, " %.0f", n ? acc[f] / n : 0.0);
+            fprintf(stderr, "\n");
+        }
+    };
+    static TimingDump td;
+    if (!td.buf) {
+        debug_dumpers().push_back([]() { td.dump(); });
+        FMB_CUDA_OK(cudaMalloc(&td.buf, (size_t)V32_TREC * V32_TFIELDS * 8));
+        FMB_CUDA_OK(cudaMalloc(&td.cnt, 4));
+        FMB_CUDA_OK(cudaMemset(td.cnt, 0, 4));
+    }
+    v32_pass_kernel<OPT, LOGT, MINB><<<lines >> LOGT, 32 << LOGT, smem, st>>>(a, td.buf, td.cnt);
+#else
+    v32_pass_kernel<OPT, LOGT, MINB><<<lines >> LOGT, 32 << LOGT, smem, st>>>(a);
+#endif
     FMB_LAUNCH_OK();
     return FMB_OK;
+}
+
+template <unsigned OPT> int launch_v32_variant(const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st) {
+    if constexpr ((OPT & FO_TWO_FFTS) != 0) {
+        switch (shape) {
+#ifndef V32_LEAN
+            case 1: return launch_v32_inst<OPT, 3, 3>(a, lines, st);
+            case 2: return launch_v32_inst<OPT, 2, 4>(a, lines, st);
+            case 3: return launch_v32_inst<OPT, 2, 5>(a, lines, st);
+            case 4: return launch_v32_inst<OPT, 2, 6>(a, lines, st);
+#endif
+            default: return launch_v32_inst<OPT, 3, 2>(a, lines, st);
+        }
+    } else {
+#ifndef V32_LEAN
+        if (shape == 1) return launch_v32_inst<OPT, 3, 3>(a, lines, st);
+#endif
+        return launch_v32_inst<OPT, 3, 2>(a, lines, st);
+    }
 }
 
 }  // namespace fmb

@@ -20,7 +20,7 @@
 //     publishes the tile's completion at GPU scope (release reduction: the fence is paid by a warp that has nothing
 //     else to do).
 //
-// Work list (fft_fused.cuh's idea, static instead of claimed): item w is tile t of pass p of column slab s, ordered
+// Work list (static assignment): item w is tile t of pass p of column slab s, ordered
 // A(s), M(s-D), C(s-2D) per step so that a slab's intermediate is produced and consumed while it is still in the L2;
 // CTA c owns items c, c+G, c+2G, ...  A tile of pass p may be requested once all tiles of pass p-1 of its slab have
 // signalled, a tile of pass A once the last pass of slab s - NSLOT has released the ring slot.  The requester and the
@@ -31,7 +31,6 @@
 #pragma once
 #include <cuda.h>
 
-#include "fft_fused.cuh"
 #include "fft_v32.cuh"
 
 namespace fmb {
@@ -56,6 +55,19 @@ struct V32PArgs {
     unsigned *done;                // [npass][nslabs] completed tiles
     unsigned long long hint_x, hint_ring;      // L2 cache policies of the two kinds of tile request
 };
+
+// Flag protocol WITHOUT L1 invalidation.  A gpu-scope acquire load or __threadfence() makes ptxas emit CCTL.IVALL, which
+// throws away the SM's whole L1 (twiddle tables included) once per tile.  It is not needed here: the data guarded by the
+// flags (the ring slots) is only ever read through the async proxy / from L2, never from L1.  So the consumer polls with
+// a relaxed load and the producer publishes with a release reduction (MEMBAR.ALL.GPU + RED, no CCTL).
+__device__ __forceinline__ unsigned ld_relaxed_gpu(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu(unsigned *p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 __device__ __forceinline__ unsigned v32p_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void v32p_mbar_init(unsigned bar, unsigned count) {
@@ -198,19 +210,11 @@ __device__ __forceinline__ void v32p_tile(const FastArgs<float2> &a, float2 *con
     };
     auto final_store = [&](int jb_, int t_) {
         const unsigned i = i0 + t_;
-        C *dst = out_col + (long long)i * a.out_is + (long long)jb_ * a.out_ks;
-        const long long kstep = (long long)32 * a.out_ks;
-        C c[4], s4 = mk<C>(1, 0);
-        if (OPT & FO_TWIDDLE) {
-            const unsigned e = i * (unsigned)jb_;
-            c[0] = cmul(__ldg(a.twL + (e & a.tw_mask)), __ldg(a.twH + (e >> a.tw_shift)));
-            const C s1 = __ldg(a.twS + i);
-            const C s2 = cmul(s1, s1);
-            c[1] = cmul(c[0], s1);
-            c[2] = cmul(c[0], s2);
-            c[3] = cmul(c[1], s2);
-            s4 = cmul(s2, s2);
-        }
+        // fixed 1024 x 1024 geometry (see v32_pass_kernel): one base register, immediate offsets
+        C *dst = out_col + (STORE_T ? (int)i + jb_ * 1024 : (int)i * 1024 + jb_);
+        constexpr int kstep = 32 * 1024;
+        V32Chain h;
+        if (OPT & FO_TWIDDLE) h = v32_chain_init(a, i, jb_);
         int klim = 0;
         if (OPT & FO_OUT_MASK) {
             const int room = a.out_n - (int)i * a.out_li;
@@ -220,8 +224,8 @@ __device__ __forceinline__ void v32p_tile(const FastArgs<float2> &a, float2 *con
         for (int q = 0; q < 32; ++q) {
             C val = v[q];
             if (OPT & FO_TWIDDLE) {
-                val = cmul(val, c[q & 3]);
-                if (q + 4 < 32) c[q & 3] = cmul(c[q & 3], s4);
+                val = cmul(val, h.c[q & 3]);
+                if (q + 4 < 32) h.c[q & 3] = cmul(h.c[q & 3], h.s4);
             }
             if (OPT & FO_OUT_CONJ) val = cconj(val);
             bool ok = true;

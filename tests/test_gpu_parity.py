@@ -669,6 +669,9 @@ def test_v32p_persistent_tma_pipeline_bit_identical_to_per_pass_kernels(fm, tmp_
         path = str(tmp_path / ('v32p_%s.pt' % mode))
         e = dict(os.environ)
         e['FMB_V32P'] = mode
+        # same arithmetic on both sides: the per-pass convolution applies the inverse transform's four-step twiddle on the
+        # last pass's loads by default, the persistent kernel on the middle pass's stores (= FMB_V32_TWM=1)
+        e['FMB_V32_TWM'] = '1'
         r = subprocess.run([sys.executable, '-c', _V32P_DUMP, path], cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
         outs[mode] = torch.load(path)
