@@ -11,7 +11,10 @@ JSON keys beyond the base contract:
   roofline     algorithmic HBM bytes of the operator (2 * 8 B * N per column) / CUDA-event time, against the
                measured copy bandwidth of MEASURED_PEAKS.json; "kernels" gives each pass's share of a step
   e2e          the same metric through the host-buffer API (Matrix.apply_host): pinned host input -> H2D -> transform ->
-               D2H, all inside the timed region, every step
+               D2H, all inside the timed region, every step, on the full column batch; per-GPU copy rates and the copy-only
+               ceiling of the same buffers measured in the same run
+  sustained    the headline step repeated back to back for >= 2 s (power-capped steady state) next to the K-step figure
+  output_check two columns of the timed batch against the reference evaluated in double precision (outside timed regions)
   cpu_baseline the reference's own CPU implementation (oracle/_ref, built from /root/reference) on this box's host
                cores, on a bounded column sample
   extras       other operators of the path at their BASELINE shapes (not the headline, same timing rules)
@@ -33,6 +36,21 @@ N = 1 << N_ORDER
 COLS = 1024
 METRIC = "circulant_forward_columns_per_s"
 UNIT = "columns/s"
+
+
+def source_hash():
+    """sha256 over the kernel sources (csrc + the C-ABI header): ties profile-derived numbers (profiles/r2_traffic.json) to
+    the code that was timed - the library itself is rebuilt on every box, its bytes are not comparable."""
+    import hashlib
+    h = hashlib.sha256()
+    src = os.path.join(ROOT, 'fastmat_b200', 'csrc')
+    for f in sorted(os.listdir(src)) + ['../../include/fastmat_b200.h']:
+        path = os.path.normpath(os.path.join(src, f))
+        if os.path.isfile(path):
+            h.update(f.encode())
+            with open(path, 'rb') as fh:
+                h.update(fh.read())
+    return h.hexdigest()[:16]
 
 
 def measured_peak():
@@ -146,6 +164,25 @@ def cpu_baseline_single(cols=16, reps=2):
             'sample': 'Circulant(2^20).forward on %d complex64 columns (F-order), best of %d, 1 process' % (cols, reps)}
 
 
+def check_against_reference(c, x_cols, y_cols):
+    """Part of the cpu_baseline leg (the checker, outside every timed region): the reference's Circulant.forward evaluated in
+    double precision (generator and input cast to complex128, SURVEY 8c rule 1) on a few columns of the timed batch,
+    compared with the GPU output of the same columns.  Returns the error normalised as the tests do:
+    max|y - y_ref| / (||x||_2 * log2 N) per column, worst column."""
+    import numpy as np
+    kind, mod = _load_reference()
+    c128 = c.astype(np.complex128)
+    x128 = np.asfortranarray(x_cols.astype(np.complex128))
+    if kind == 'reference':
+        ref = mod.Circulant(c128).forward(x128)
+    else:
+        ref = mod.circulant_forward(c128, x128, double=True)
+    err = np.abs(y_cols.astype(np.complex128) - ref).max(axis=0)
+    norm = np.sqrt((np.abs(x128) ** 2).sum(axis=0)) * N_ORDER
+    return {'columns_checked': int(x_cols.shape[1]), 'max_err_over_norm_x_log2n': float((err / norm).max()),
+            'tolerance': 1e-5, 'reference': kind + ' in complex128', 'ok': bool((err / norm).max() <= 1e-5)}
+
+
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation on all host cores (one worker process per core, disjoint
     column shards), same metric / config; each step is a bounded sample of the workload."""
@@ -225,6 +262,8 @@ def run_ours(args):
 
     cols = args.cols
     steps, warm = max(1, args.steps), max(3, args.warmup)
+    from fastmat_b200 import parallel as fpar
+    cores = fpar.bind_to_gpu_numa(local_rank) if distributed else None      # before any pinned allocation
     rng = np.random.default_rng(4321)
     c = (rng.standard_normal(N) + 1j * rng.standard_normal(N)).astype(np.complex64)
     C = fm.Circulant(c)
@@ -239,7 +278,9 @@ def run_ours(args):
 
     x = crandn(N, cols)
 
-    def timed(fn, k, w):
+    def timed(fn, k, w, sustain_s=0.0):
+        """ms per step over k steps (max over ranks); with sustain_s > 0 additionally the mean over a back-to-back run of at
+        least that many seconds (the power-capped steady state)."""
         for _ in range(w):
             fn()
         barrier()
@@ -249,11 +290,19 @@ def run_ours(args):
             fn()
         e1.record()
         barrier()
-        return max_over_ranks(e0.elapsed_time(e1)) / k          # ms per step, max over ranks
+        ms = max_over_ranks(e0.elapsed_time(e1)) / k          # ms per step, max over ranks
+        if sustain_s <= 0:
+            return ms, None
+        n = max(k, int(sustain_s * 1e3 / ms) + 1)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        return ms, max_over_ranks(e0.elapsed_time(e1)) / n
 
     # ---- headline: device-resident inputs
     sampler = ClockSampler(local_rank)
-    launches0 = fm.launch_count()
     for _ in range(warm):
         y = C.forward(x)
     barrier()
@@ -265,98 +314,161 @@ def run_ours(args):
         y = C.forward(x)
     e1.record()
     barrier()
-    clocks = sampler.stop()
     launches = fm.launch_count() - launches0
     ms = max_over_ranks(e0.elapsed_time(e1)) / steps
+    # the same loop back to back for >= args.sustain seconds: what the operator holds under the power cap
+    n_sus = max(steps, int(args.sustain * 1e3 / ms) + 1) if args.sustain > 0 else 0
+    ms_sus = None
+    if n_sus:
+        e0.record()
+        for _ in range(n_sus):
+            y = C.forward(x)
+        e1.record()
+        barrier()
+        ms_sus = max_over_ranks(e0.elapsed_time(e1)) / n_sus
+    clocks = sampler.stop()
     value = world * cols / (ms * 1e-3)
     peak, peak_src = measured_peak()
     alg_bytes = 2.0 * 8.0 * N * cols                             # read x + write y, per GPU and step
     achieved = alg_bytes / (ms * 1e-3) / 1e9
     info = C._plan.info
 
-    # per-kernel share of a step and DRAM traffic: from the committed ncu launch list of this same command
-    # (profiles/r1_traffic.json <- profiles/r1_launches_bench_circulant.csv); live numbers above are CUDA events only
-    traffic = None
-    kernels = {}
-    dominant = None
+    # per-kernel share of a step and DRAM traffic come from the ncu launch list of this command committed under profiles/;
+    # they are quoted only if that list was captured on the kernel sources being timed now (source hash), else null + why
+    traffic, kernels, dominant, prof_note = None, None, None, None
+    shash = source_hash()
     try:
-        with open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')) as f:
+        with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
             tj = json.load(f)
-        if cols == COLS:
-            traffic = tj['dram_bytes_per_step']
-        kernels = {k: {'share_of_step_time': v['share_of_step_time'], 'avg_us_under_ncu': v['avg_us']}
-                   for k, v in tj['kernels'].items() if v['share_of_step_time'] > 0.01}
-        dominant = tj.get('dominant_kernel')
-    except Exception:
-        pass
+        if tj.get('source_hash') != shash:
+            prof_note = 'profiles/r2_traffic.json was captured on other kernel sources (%s, timed now: %s): not quoted' % (tj.get('source_hash'), shash)
+        else:
+            if cols == COLS:
+                traffic = tj['dram_bytes_per_step']
+            kernels = {k: {'share_of_step_time': v['share_of_step_time'], 'avg_us_under_ncu': v['avg_us']}
+                       for k, v in tj['kernels'].items() if v['share_of_step_time'] > 0.01}
+            dominant = tj.get('dominant_kernel')
+            prof_note = 'from profiles/r2_traffic.json (ncu launch list of this command, same kernel sources: %s)' % shash
+    except Exception as e:
+        prof_note = 'profiles/r2_traffic.json not readable (%s)' % (e.__class__.__name__, )
+
+    # columns of the timed batch kept for the check against the reference (cpu_baseline leg, rank 0)
+    chk_cols = 2
+    x_chk = x[:, :chk_cols].cpu().numpy() if rank == 0 else None
+    y_chk = y[:, :chk_cols].cpu().numpy() if rank == 0 else None
+    y_dtype = y.dtype
     del y
 
-    # ---- e2e: host buffers through Matrix.apply_host (H2D + transform + D2H inside the timed region)
+    # ---- e2e: host buffers through Matrix.apply_host (H2D + transform + D2H inside the timed region, every step)
     e2e = None
     if not args.no_e2e:
         e2e_cols = min(cols, args.e2e_cols)
+        avail_gib = 0.0
+        try:
+            with open('/proc/meminfo') as f:
+                for ln in f:
+                    if ln.startswith('MemAvailable'):
+                        avail_gib = float(ln.split()[1]) / 2 ** 20
+        except Exception:
+            pass
+        need_gib = 2 * 8.0 * N * e2e_cols / 2 ** 30 * world
+        while avail_gib and need_gib > 0.5 * avail_gib and e2e_cols > 64:      # pinned staging must fit the host comfortably
+            e2e_cols //= 2
+            need_gib /= 2
         xh = torch.empty((e2e_cols, N), dtype=torch.complex64, pin_memory=True).t()
         xh.copy_(x[:, :e2e_cols])
-        yh = torch.empty((e2e_cols, N), dtype=torch.complex64, pin_memory=True).t()
-        k_e2e = max(1, min(steps, 3))
+        yh = torch.empty((e2e_cols, N), dtype=y_dtype, pin_memory=True).t()
+        k_e2e = max(1, min(steps, args.e2e_steps))
+        st = {}
         C.apply_host(xh, out=yh)
         barrier()
         t0 = time.perf_counter()
         for _ in range(k_e2e):
-            C.apply_host(xh, out=yh)
+            C.apply_host(xh, out=yh, stats=st)
         torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        dt = max_over_ranks(dt)
-        e2e = {'value': world * e2e_cols * k_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(8 * N * e2e_cols),
-               'd2h_bytes_per_step': int(8 * N * e2e_cols), 'columns_per_step_per_gpu': e2e_cols, 'steps': k_e2e,
+        dt = max_over_ranks(time.perf_counter() - t0)
+        # copy-only ceiling of the same buffers (nothing computed): what the host path could reach if the transform were free
+        barrier()
+        ct, cb_in, cb_out = fpar.host_copy_ceiling(xh, yh, dev)
+        ct = max_over_ranks(ct)
+        e2e = {'value': world * e2e_cols * k_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': int(st['h2d_bytes']),
+               'd2h_bytes_per_step': int(st['d2h_bytes']), 'columns_per_step_per_gpu': e2e_cols, 'steps': k_e2e,
+               'h2d_gbs_per_gpu': st['h2d_bytes'] * k_e2e / dt / 1e9, 'd2h_gbs_per_gpu': st['d2h_bytes'] * k_e2e / dt / 1e9,
+               'copy_only_ceiling': {'value': world * e2e_cols / ct, 'unit': UNIT, 'h2d_gbs_per_gpu': cb_in / ct / 1e9,
+                                     'd2h_gbs_per_gpu': cb_out / ct / 1e9,
+                                     'note': 'same pinned buffers and chunking, both directions at once, no transform; max over ranks'},
+               'fraction_of_copy_ceiling': (world * e2e_cols * k_e2e / dt) / (world * e2e_cols / ct),
+               'host_cores_bound': (len(cores) if cores else None),
                'api': 'Circulant.apply_host(pinned CPU tensor) == Circulant.forward(host array)'}
         del xh, yh
 
-    # ---- extras: the other operators of the path at their BASELINE shapes
+    # ---- extras: the other operators of the path at their BASELINE shapes, 20-step and sustained figures
     extras = {}
     if rank == 0 and not args.quick and not distributed:
         k2 = max(3, steps // 2)
+        sus = min(args.sustain, 1.0)
 
-        def rec(name, ms_, ncols, bytes_per_col):
-            extras[name] = {'ms_per_step': ms_, 'columns_per_s': ncols / (ms_ * 1e-3),
-                            'hbm_gbs': bytes_per_col * ncols / (ms_ * 1e-3) / 1e9,
-                            'roofline_frac': bytes_per_col * ncols / (ms_ * 1e-3) / 1e9 / peak}
-        rec('circulant_backward_2^20_c64', timed(lambda: C.backward(x), k2, 3), cols, 16.0 * N)
+        def rec(name, fn, ncols, bytes_per_col, k=None, w=3, sustain=None):
+            try:
+                ms_, ms_s = timed(fn, k or k2, w, sus if sustain is None else sustain)
+                r = {'ms_per_step': ms_, 'columns': ncols, 'columns_per_s': ncols / (ms_ * 1e-3),
+                     'hbm_gbs': bytes_per_col * ncols / (ms_ * 1e-3) / 1e9,
+                     'roofline_frac': bytes_per_col * ncols / (ms_ * 1e-3) / 1e9 / peak}
+                if ms_s is not None:
+                    r['sustained_ms_per_step'] = ms_s
+                    r['sustained_roofline_frac'] = bytes_per_col * ncols / (ms_s * 1e-3) / 1e9 / peak
+                extras[name] = r
+            except Exception as e:                                  # a secondary row must not take the headline down
+                extras[name] = {'error': repr(e)}
+                torch.cuda.synchronize()
+
+        rec('circulant_backward_2^20_c64', lambda: C.backward(x), cols, 16.0 * N)
         F = fm.Fourier(N)
-        rec('fourier_forward_2^20_c64', timed(lambda: F.forward(x), k2, 3), cols, 16.0 * N)
+        rec('fourier_forward_2^20_c64', lambda: F.forward(x), cols, 16.0 * N)
+        K = fm.Kron(fm.Fourier(1024), fm.Fourier(1024))
+        rec('kron_fourier_1024x1024_c64', lambda: K.forward(x), cols, 16.0 * N)
+        # torch's default row-major layout (batch contiguous): SURVEY 8d asks for both layouts
+        xr = x.contiguous()
+        rec('circulant_forward_2^20_c64_row_major', lambda: C.forward(xr), cols, 16.0 * N, k=2, w=1, sustain=0)
+        rec('fourier_forward_2^20_c64_row_major', lambda: F.forward(xr), cols, 16.0 * N, k=2, w=1, sustain=0)
+        del xr
         nt = 1 << 19
         vc = (rng.standard_normal(nt) + 1j * rng.standard_normal(nt)).astype(np.complex64)
         vr = (rng.standard_normal(nt - 1) + 1j * rng.standard_normal(nt - 1)).astype(np.complex64)
         T = fm.Toeplitz(vc, vr)
-        xt = x[:nt, :]
-        xt = xt.t().contiguous().t()
-        rec('toeplitz_forward_2^19_c64', timed(lambda: T.forward(xt), k2, 3), cols, 8.0 * 2 * nt)
-        rec('toeplitz_backward_2^19_c64', timed(lambda: T.backward(xt), k2, 3), cols, 8.0 * 2 * nt)
+        xt = x[:nt, :].t().contiguous().t()
+        rec('toeplitz_forward_2^19_c64', lambda: T.forward(xt), cols, 8.0 * 2 * nt)
+        rec('toeplitz_backward_2^19_c64', lambda: T.backward(xt), cols, 8.0 * 2 * nt)
         del xt
-        K = fm.Kron(fm.Fourier(1024), fm.Fourier(1024))
-        rec('kron_fourier_1024x1024_c64', timed(lambda: K.forward(x), k2, 3), cols, 16.0 * N)
+        Fb = fm.Fourier(1000003)
+        xb = x[:1000003, :].t().contiguous().t()
+        rec('fourier_bluestein_1000003_c64', lambda: Fb.forward(xb), cols, 16.0 * 1000003, k=3, w=2)
+        del xb
         Hd = fm.Hadamard(20)
-        xf = torch.view_as_real(x.t().contiguous()).reshape(cols * 2, N).t()             # (2^20, 2048) float32, column-major
-        rec('hadamard_forward_o20_f32', timed(lambda: Hd.forward(xf), k2, 3), xf.shape[1], 8.0 * N)
-        try:            # scatter -> FWHT(order 20) -> gather, three launches; 2 x 4 B x (2^20 - 1) per column
+        xf = torch.empty((4 * cols, N), dtype=torch.float32, device=dev).normal_(generator=g).t()   # (2^20, 4096) float32, column-major
+        rec('hadamard_forward_o20_f32', lambda: Hd.forward(xf), xf.shape[1], 8.0 * N)
+        try:            # scatter -> FWHT(order 20) -> gather; 2 x 4 B x (2^20 - 1) per column
             Ll = fm.LFSRCirculant((1 << 20) | (1 << 3) | 1, 1)
             xl = xf[:N - 1, :1024].t().contiguous().t()
-            rec('lfsr_circulant_forward_o20_f32', timed(lambda: Ll.forward(xl), k2, 3), xl.shape[1], 8.0 * (N - 1))
+            rec('lfsr_circulant_forward_o20_f32', lambda: Ll.forward(xl), xl.shape[1], 8.0 * (N - 1))
             del xl, Ll
-        except Exception as e:                                     # a secondary row must not take the headline down
+        except Exception as e:
             extras['lfsr_circulant_forward_o20_f32'] = {'error': repr(e)}
         del xf
-        Fb = fm.Fourier(1000003)
-        xb = x[:1000003, :256].t().contiguous().t()
-        rec('fourier_bluestein_1000003_c64', timed(lambda: Fb.forward(xb), 3, 2), 256, 16.0 * 1000003)
-        del xb
         x16 = crandn(1 << 16, 64).to(torch.complex128)
         F16 = fm.Fourier(1 << 16)
-        rec('fourier_forward_2^16_c128_64cols', timed(lambda: F16.forward(x16), 10, 3), 64, 32.0 * (1 << 16))
+        rec('fourier_forward_2^16_c128_64cols', lambda: F16.forward(x16), 64, 32.0 * (1 << 16), k=20)
+        del x16
 
     cpu = None
+    check = None
     if rank == 0 and not args.no_cpu and not distributed:          # reported at N = 1 only
         cpu = cpu_baseline_single(cols=args.cpu_cols, reps=2)
+    if rank == 0 and not args.no_cpu:
+        try:
+            check = check_against_reference(c, x_chk, y_chk)
+        except Exception as e:
+            check = {'error': repr(e)}
 
     if rank == 0:
         line = {
@@ -369,6 +481,10 @@ def run_ours(args):
                        'l2': 'inputs per step (%.1f GiB) exceed the 126 MB L2, no flush needed' % (8.0 * N * cols / 2 ** 30),
                        'inner_fft': int(info.inner_size), 'passes_per_slab': int(info.passes_fwd), 'slab_cols': int(info.slab_cols)},
             'clocks': clocks,
+            'sustained': (None if ms_sus is None else
+                          {'ms_per_step': ms_sus, 'steps': n_sus, 'value': world * cols / (ms_sus * 1e-3), 'unit': UNIT,
+                           'roofline_frac': alg_bytes / (ms_sus * 1e-3) / 1e9 / peak,
+                           'note': 'the same step repeated back to back for >= %.1f s (power-capped steady state)' % args.sustain}),
             'e2e': e2e,
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
@@ -377,12 +493,12 @@ def run_ours(args):
                          'note': ('operator level: algorithmic bytes of one step (2 x 8 B x N per column, SURVEY 8d) / CUDA-event '
                                   'time of the step on the caller stream; one step = %d launches (3 passes per slab of %d columns, '
                                   'slabs issued round-robin on internal streams so a per-kernel event time does not exist); '
-                                  'kernels = each pass kernel\'s share of the step and traffic = DRAM bytes per step, both from '
-                                  'the committed ncu launch list of this command (profiles/r1_traffic.json)')
-                                 % (launches // steps, int(info.slab_cols)),
+                                  'kernels / traffic: ' % (launches // steps, int(info.slab_cols))) + str(prof_note),
                          'dominant_kernel': dominant,
                          'launches_per_step': launches // steps,
-                         'kernels': kernels},
+                         'kernels': kernels,
+                         'kernel_source_hash': shash},
+            'output_check': check,
             'cpu_baseline': cpu,
             'extras': extras,
         }
@@ -399,7 +515,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--cols', type=int, default=COLS)
-    ap.add_argument('--e2e-cols', type=int, default=256, dest='e2e_cols')
+    ap.add_argument('--e2e-cols', type=int, default=COLS, dest='e2e_cols', help='columns per GPU of the host-buffer (e2e) step')
+    ap.add_argument('--e2e-steps', type=int, default=2, dest='e2e_steps')
+    ap.add_argument('--sustain', type=float, default=2.0, help='seconds of back-to-back steps for the sustained figure (0: off)')
     ap.add_argument('--cpu-cols', type=int, default=16, dest='cpu_cols')
     ap.add_argument('--quick', action='store_true', help='headline only (no extras)')
     ap.add_argument('--no-e2e', action='store_true', dest='no_e2e')

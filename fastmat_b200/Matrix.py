@@ -38,6 +38,26 @@ def alloc_out(rows, cols, torch_dtype, device, row_major):
     return torch.empty((cols, rows), dtype=torch_dtype, device=device).t()      # column-major (rows, cols)
 
 
+_HOST_CTX = {}
+_HOST_STREAMS = {}
+
+
+def _host_context(dev, rows, step, dtype, row_major):
+    """Copy streams (one pair per device) and device staging buffers (per slab shape) of ``apply_host``."""
+    key = (dev.index, rows, step, dtype, row_major)
+    ctx = _HOST_CTX.get(key)
+    if ctx is None:
+        if len(_HOST_CTX) >= 8:                      # staging buffers are up to 2 x 64 MiB: keep a handful of shapes
+            _HOST_CTX.pop(next(iter(_HOST_CTX)))
+        streams = _HOST_STREAMS.get(dev.index)
+        if streams is None:
+            streams = _HOST_STREAMS[dev.index] = (torch.cuda.Stream(dev), torch.cuda.Stream(dev))
+        ctx = {'s_in': streams[0], 's_out': streams[1],
+               'bufs': [alloc_out(rows, step, dtype, dev, row_major) for _ in range(2)], 'free': [None, None]}
+        _HOST_CTX[key] = ctx
+    return ctx
+
+
 def _ptr(t):
     return t.data_ptr() if t.numel() > 0 else None
 
@@ -244,14 +264,16 @@ class Matrix(object):
         x, ndim, np_out = self._prepare(arrX, self.numRows)
         return self._finish(self._backward(x), ndim, np_out)
 
-    def apply_host(self, arrX, backward=False, out=None, chunk_bytes=64 << 20):
+    def apply_host(self, arrX, backward=False, out=None, chunk_bytes=64 << 20, stats=None):
         """Host buffers in, host buffers out: the call a user with numpy data makes (``M.forward(ndarray)``).
 
         The column batch is cut into slabs of ``chunk_bytes`` (64 MiB: the fill and drain of the pipeline cost one slab each;
         measured on B200 / PCIe 5: 5.46 k columns/s against 5.07 k with 256 MiB slabs, tools/e2e_chunks.py); slab k+1 is
-        copied host->device while slab k is transformed and slab k-1 is copied device->host (three streams, double-buffered).  ``arrX`` may be a numpy array or a CPU torch tensor
-        (pinned memory makes the copies asynchronous); ``out`` an optional preallocated CPU tensor / array of the
-        result shape.  Returns the same kind of object that came in.
+        copied host->device while slab k is transformed and slab k-1 is copied device->host.  The two copy streams and the
+        two device staging buffers are created once per (device, slab shape) and reused by every later call on any matrix
+        (round 1 created streams per call).  ``arrX`` may be a numpy array or a CPU torch tensor (pinned memory makes the
+        copies asynchronous); ``out`` an optional preallocated CPU tensor / array of the result shape.  Returns the same kind
+        of object that came in.  ``stats`` (a dict) receives the bytes moved in each direction.
         """
         is_np = isinstance(arrX, np.ndarray)
         xh = torch.from_numpy(arrX) if is_np else arrX
@@ -270,14 +292,15 @@ class Matrix(object):
         rows_out = self.numCols if backward else self.numRows
         step = max(1, min(max(M, 1), chunk_bytes // max(1, required * x2.element_size())))
         cur = torch.cuda.current_stream(dev)
-        s_in, s_out = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        bufs = [None, None]
-        free_ev = [None, None]
+        ctx = _host_context(dev, required, step, x2.dtype, is_row_major(x2))
+        s_in, s_out, bufs, free_ev = ctx['s_in'], ctx['s_out'], ctx['bufs'], ctx['free']
+        # a previous call may still be draining on the copy streams: order this call behind it
+        s_in.wait_stream(cur)
         out_h = None
         if out is not None:
             out_h = torch.from_numpy(out) if isinstance(out, np.ndarray) else out
             out_h = out_h.reshape(rows_out, -1)
-        pending = []
+        h2d = d2h = 0
         for k, c0 in enumerate(range(0, max(M, 1), step)):
             c1 = min(M, c0 + step)
             if c1 <= c0:
@@ -286,28 +309,29 @@ class Matrix(object):
             with torch.cuda.stream(s_in):
                 if free_ev[b] is not None:
                     s_in.wait_event(free_ev[b])
-                if bufs[b] is None or bufs[b].shape[1] < c1 - c0:
-                    bufs[b] = alloc_out(required, step, x2.dtype, dev, is_row_major(x2))
                 xd = bufs[b][:, :c1 - c0]
                 xd.copy_(x2[:, c0:c1], non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(s_in)
+            h2d += xd.numel() * xd.element_size()
             cur.wait_event(ready)
             xp, _, _ = self._prepare(xd, required)
             yd = self._backward(xp) if backward else self._forward(xp)
             free_ev[b] = torch.cuda.Event()
             free_ev[b].record(cur)
-            done = torch.cuda.Event()
-            done.record(cur)
             if out_h is None:
                 out_h = torch.empty((M, rows_out), dtype=yd.dtype, pin_memory=xh.is_pinned()).t() if not is_row_major(x2) \
                     else torch.empty((rows_out, M), dtype=yd.dtype, pin_memory=xh.is_pinned())
             with torch.cuda.stream(s_out):
-                s_out.wait_event(done)
+                s_out.wait_event(free_ev[b])
                 out_h[:, c0:c1].copy_(yd, non_blocking=True)
                 yd.record_stream(s_out)
-            pending.append(yd)
+            d2h += yd.numel() * yd.element_size()
         s_out.synchronize()
+        if stats is not None:
+            stats['h2d_bytes'] = h2d
+            stats['d2h_bytes'] = d2h
+            stats['chunks'] = (max(M, 1) + step - 1) // step
         if out_h is None:
             out_h = torch.empty((rows_out, M), dtype=_t.getTorchType(self._fusedType))
         res = out_h.reshape(-1) if ndim == 1 else out_h

@@ -642,6 +642,10 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
             a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
             a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[0].p;
             a.pre = pre_d;
+            // L2 prefetch of the input of the slab `pf_ahead` slabs later (full slabs of full columns only)
+            static const long pf_ahead = env_long("FMB_V32_PF", 0);
+            if (pf_ahead > 0 && rows_in == L && c0 + (pf_ahead + 1) * slab <= M && nc == slab)
+                a.pf = (const C *)x + (c0 + pf_ahead * slab) * xcs;
             unsigned opt;
             if (!two_ffts) opt = bwd ? V32_A_FC : V32_A_F;
             else if (pre_d) opt = bwd ? V32_A_MPC : V32_A_MP;

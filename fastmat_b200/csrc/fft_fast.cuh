@@ -60,6 +60,7 @@ template <typename C> struct FastArgs {
     const C *mid;                // spectrum, transposed at plan creation: element (k, i) at mid[i*mid_is + k]
     int mid_is;
     const C *pre, *post;         // indexed by logical row
+    const C *pf;                 // V32 first pass: same tile position in the slab whose input should be pulled into L2 now (or null)
 };
 
 // option bits of a pass

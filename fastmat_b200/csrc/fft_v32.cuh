@@ -167,6 +167,12 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
     int jb, t;
 
     V32_T_MARK(0.f);
+    if constexpr (LOAD_T && STORE_T && (OPT & FO_TWIDDLE)) {
+        // first pass: ask the L2 for the 64 KB of a LATER slab's input that correspond to this tile's share (the 128 tiles
+        // of a column cover it in contiguous chunks), so that slab's loads find their data on chip (FMB_V32_PF, experiments)
+        if (a.pf != nullptr && tid == 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(a.pf + (long long)col * a.in_cs + (long long)(i0 >> 3) * 8192), "r"(65536u) : "memory");
+    }
     // Stage twiddles are read through L1 where they are needed.  Measured alternatives (round 2, profiles/r2_experiments.txt):
     // copying the 8 KB table into shared memory with cp.async at the start of the CTA shortens the second stage (the L1 is
     // cold after every launch boundary) but the copy competes with the tile's own loads: +4 % overall; requesting the
@@ -230,11 +236,11 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
     exchange_store(jb, t);
 
     // second radix-32 stage: v[m] <- position jb + 32 m, times W_1024^{jb m}, DFT; leaves X[jb + 32 q] in v[q]
-    auto stage_b = [&](int jb_, int t_) {
+    auto stage_b = [&](int jb_, int t_, const CPair<C> *tb) {
         const C *sl = smem + t_ * V32_RS + jb_;
 #pragma unroll
         for (int m = 0; m < 32; ++m) v[m] = sl[33 * m];
-        const CPair<C> *tp = tab + jb_;
+        const CPair<C> *tp = tb + jb_;
 #pragma unroll
         for (int p2 = 0; p2 < 16; ++p2) {
 #ifdef V32_DEBUG_NOTW                                                   /* timing experiment only */
@@ -292,7 +298,7 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
         v32_sync<WARP_ONLY_1>();
         V32_T_MARK(0.f);                                                // exchange stores issued, barrier passed
         v32_pos<STORE_T, LOGT>(tid, jb, t);
-        stage_b(jb, t);
+        stage_b(jb, t, tab);
         V32_T_MARK(v[0].x + v[31].y);                                   // second stage done
         final_store(jb, t);
         V32_T_MARK(0.f);                                                // stores issued
@@ -308,7 +314,7 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
         C mh[16];
 #pragma unroll
         for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r));
-        stage_b(jb, t);
+        stage_b(jb, t, tab);
         V32_T_MARK(v[0].x + v[31].y);                                   // first transform done
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[2 * r] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r], mh[r]) : cmul(v[2 * r], mh[r]));
@@ -326,7 +332,9 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
         v32_sync<!STORE_T>();
         v32_pos<STORE_T, LOGT>(tid, jb, t);
         V32_T_MARK(0.f);
-        stage_b(jb, t);                       // (the twiddle loads are volatile asm: not merged with the first transform's)
+        // second copy of the table: the compiler merges loads from identical addresses with the first transform's and then
+        // keeps all sixteen pairs (64 registers) alive across the pass - measured (round 2, by accident): 2.30 -> 3.25 ms
+        stage_b(jb, t, tab + 512);
         V32_T_MARK(v[0].x + v[31].y);
         final_store(jb, t);
         V32_T_MARK(0.f);

@@ -91,3 +91,53 @@ def gather_columns(y_local, num_cols, dst=None, group=None):
         out[c0:c0 + widths[r]] = blk[:widths[r]]
         c0 += widths[r]
     return out.t()                      # (n, num_cols), column-major like every result of the apply path
+
+
+def bind_to_gpu_numa(device_index):
+    """Restrict this process to the host cores NVML reports as local to GPU ``device_index`` (sched_setaffinity), so that
+    pinned staging buffers allocated afterwards are first-touched on that GPU's NUMA node and the copy threads run next to
+    its PCIe root.  Host-path (apply_host) scaling over the GPUs of one box depends on it when the box has several NUMA
+    nodes; a no-op (returns None) when NVML or the affinity call is unavailable.  Returns the sorted core list."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cores = [w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and w * 64 + b < ncpu]
+        if not cores:
+            return None
+        allowed = sorted(set(cores) & set(os.sched_getaffinity(0))) or sorted(cores)
+        os.sched_setaffinity(0, allowed)
+        return allowed
+    except Exception:
+        return None
+
+
+def host_copy_ceiling(x_host, y_host, device, chunk_bytes=64 << 20, repeats=1):
+    """Copy-only ceiling of the host path on this rank: the input batch host->device and an equally chunked output batch
+    device->host, on two streams at once, nothing computed.  Returns (seconds, h2d_bytes, d2h_bytes) - what apply_host
+    could reach if the transform were free."""
+    import time
+    rows, M = x_host.shape
+    step = max(1, min(M, chunk_bytes // max(1, rows * x_host.element_size())))
+    s_in, s_out = torch.cuda.Stream(device), torch.cuda.Stream(device)
+    col_major = not (x_host.shape[1] > 1 and x_host.stride(1) == 1 and x_host.stride(0) != 1)
+    def dev_buf(r, c, dt):
+        return torch.empty((c, r), dtype=dt, device=device).t() if col_major else torch.empty((r, c), dtype=dt, device=device)
+    din = [dev_buf(rows, step, x_host.dtype) for _ in range(2)]
+    dout = [dev_buf(y_host.shape[0], step, y_host.dtype) for _ in range(2)]
+    torch.cuda.synchronize(device)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        for k, c0 in enumerate(range(0, M, step)):
+            c1 = min(M, c0 + step)
+            with torch.cuda.stream(s_in):
+                din[k % 2][:, :c1 - c0].copy_(x_host[:, c0:c1], non_blocking=True)
+            with torch.cuda.stream(s_out):
+                y_host[:, c0:c1].copy_(dout[k % 2][:, :c1 - c0], non_blocking=True)
+    s_in.synchronize()
+    s_out.synchronize()
+    dt = (time.perf_counter() - t0) / repeats
+    return dt, x_host.numel() * x_host.element_size(), y_host.numel() * y_host.element_size()

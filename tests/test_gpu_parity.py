@@ -706,3 +706,52 @@ def test_v32p_apply_in_cuda_graph(fm):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(y, eager * 2.0)
+
+
+# ------------------------------------------------------------------------------------------- round-2 advisor items
+@pytest.mark.gpu
+def test_dense_matrix_uses_numpy_promotion_not_torch(fm):
+    """fastmat's promotion table is np.promote_types (fastmat/core/types.pyx:443-453): an int32 / int64 matrix applied to
+    float32 data is float64 (torch.promote_types would say float32 and lose integers above 2^24), integer x integer wraps
+    like numpy.  Blocks accumulates its terms in the same table."""
+    rng = np.random.default_rng(5)
+    a = rng.integers(2 ** 24, 2 ** 26, size=(6, 5)).astype(np.int32)
+    x = rng.integers(1, 4, size=(5, 3)).astype(np.float32)
+    M = fm.Matrix(torch.from_numpy(a))
+    y = M.forward(torch.from_numpy(x).cuda())
+    ref = a.astype(np.float64) @ x.astype(np.float64)
+    assert y.dtype == torch.float64 and np.array_equal(y.cpu().numpy(), ref)
+    yb = M.backward(torch.from_numpy(ref.astype(np.float32)).cuda())
+    assert yb.dtype == torch.float64
+    xi = rng.integers(-2 ** 40, 2 ** 40, size=(5, 2)).astype(np.int64)
+    a64 = rng.integers(-2 ** 40, 2 ** 40, size=(4, 5)).astype(np.int64)
+    yi = fm.Matrix(torch.from_numpy(a64)).forward(torch.from_numpy(xi).cuda())
+    assert yi.dtype == torch.int64 and np.array_equal(yi.cpu().numpy(), a64 @ xi)          # wraps exactly like numpy
+    B = fm.Blocks([[fm.Matrix(torch.from_numpy(a)), fm.Matrix(torch.from_numpy(a))]])
+    xb = torch.from_numpy(np.vstack([x, x])).cuda()
+    yB = B.forward(xb)
+    assert yB.dtype == torch.float64 and np.array_equal(yB.cpu().numpy(), 2 * ref)
+
+
+@pytest.mark.gpu
+def test_product_python_scalars_are_weakly_typed(fm):
+    """The operator dtype never depends on a scalar's VALUE (NEP 50 semantics): M * 0.5 and M * 0.1, M / 2 and M / 3 have the
+    same dtype; a python scalar lifts integer operators to the reference's int64 / float64 / complex128
+    (np.array(scalar).dtype, fastmat/Product.pyx:108-114) and leaves the precision of floating operators alone; numpy
+    scalars keep their dtype."""
+    rng = np.random.default_rng(6)
+    c = (rng.standard_normal(16) + 1j * rng.standard_normal(16)).astype(np.complex64)
+    C = fm.Circulant(c)
+    assert (C * 0.5).dtype == (C * 0.1).dtype == (C / 2).dtype == (C / 3).dtype == np.complex64
+    assert (2 * C).dtype == np.complex64 and (C * 2j).dtype == np.complex64
+    assert (C * np.float64(0.5)).dtype == np.complex128
+    H = fm.Hadamard(3)
+    # integer operators: python int -> int64, then Product's safe type expansion (types.pyx:378-394) makes it float64
+    assert (H * 2).dtype == (H / 2).dtype == (H / 3).dtype == np.float64 and (H * 1j).dtype == np.complex128
+    assert (H * np.int8(2)).dtype == np.float32                                  # int8 x int8 -> int8 -> expanded to float32
+    assert fm.Product(H, 2, typeExpansion=None).dtype == np.int64 and fm.Product(H, np.int8(2), typeExpansion=None).dtype == np.int8
+    D = fm.Diag(np.arange(1, 9, dtype=np.float32))
+    assert (D * 0.1).dtype == np.float32 and (D * 1j).dtype == np.complex64
+    x = torch.from_numpy(rng.standard_normal((16, 2)).astype(np.float32)).cuda().to(torch.complex64)
+    y1, y2 = (C / 3).forward(x), C.forward(x) / 3
+    assert y1.dtype == torch.complex64 and float((y1 - y2).abs().max()) <= 1e-5 * float(y2.abs().max())

@@ -2,14 +2,18 @@
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
         --log-file launches.csv python bench.py --steps 2 --warmup 1 --quick --no-e2e --no-cpu
-    python tools/traffic_from_launches.py launches.csv profiles/r1_traffic.json <launches of EACH pass kernel per step>
+    python tools/traffic_from_launches.py launches.csv profiles/r2_traffic.json <launches of EACH pass kernel per step>
 
 ncu serialises the launches and flushes caches between them, so absolute times are cold-cache; what bench.py quotes
 from here is each kernel's SHARE of a step and the DRAM bytes per step.
 """
 import csv
 import json
+import os
 import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from bench import source_hash            # noqa: E402  (ties the profile to the kernel sources it was captured on)
 
 src, dst, per_step = sys.argv[1], sys.argv[2], int(sys.argv[3])
 rows = list(csv.reader(open(src)))
@@ -38,7 +42,7 @@ tot_ns = sum(v['ns'] for v in ours.values())
 N, COLS = 1 << 20, 1024
 out = {'source': src + ' (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; '
                    'bench.py --quick; the capture covers part of the run, per-step figures = per-launch averages x %d launches of each pass per step)' % per_step,
-       'workload': 'Circulant(2^20).forward, complex64, 1024 columns', 'kernels': {}}
+       'workload': 'Circulant(2^20).forward, complex64, 1024 columns', 'source_hash': source_hash(), 'kernels': {}}
 for k, v in sorted(ours.items(), key=lambda t: -t[1]['ns']):
     n = len(v['ids'])
     out['kernels'][k] = {'launches_captured': n, 'launches_per_step': per_step, 'share_of_step_time': v['ns'] / tot_ns,
