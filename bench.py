@@ -229,6 +229,59 @@ def run_reference_arm(args):
     return 0
 
 
+# ------------------------------------------------------------------------------------------- config 5 (solvers)
+def run_config5(fm, fpar, dev, rank, world, distributed, barrier, max_over_ranks, cols_per_gpu):
+    """fastmat.algorithms ISTA (100 steps) and OMP (k = 32) on the compressed-sensing operator of BASELINE config 5, one
+    shard of right-hand sides per GPU through parallel.solve_sharded; reports columns solved per second (whole job) and
+    checks the recovery (OMP: exact support)."""
+    import numpy as np
+    import torch
+    n, m, k = 1 << 18, 1 << 16, 32
+    rng = np.random.default_rng(2026)                                    # the operator is the same on every rank
+    rows = np.sort(rng.choice(n, m, replace=False))
+    d = np.exp(2j * np.pi * rng.random(n)).astype(np.complex64)
+    A = fm.Product(fm.Partial(fm.Fourier(n), rows=rows), fm.Diag(d))
+    L = cols_per_gpu
+    rl = np.random.default_rng(7000 + rank)                              # every rank has its own right-hand sides
+    x = np.zeros((L, n), dtype=np.complex64)
+    for c in range(L):
+        idx = rl.choice(n, k, replace=False)
+        x[c, idx] = (2 + rl.random(k)) * np.exp(2j * np.pi * rl.random(k))
+    xd = torch.from_numpy(x).to(dev).t()                                 # column-major (n, L)
+    b = A.forward(xd)
+    out = {'operator': 'Product(Partial(Fourier(2^18), 2^16 sorted random rows), Diag(unit modulus)), complex64',
+           'columns_per_gpu': L, 'global_columns': L * world, 'sparsity': k,
+           'sharding': 'parallel.solve_sharded: one shard of right-hand sides per GPU, no collective in the iteration'}
+
+    def wall(fn):
+        barrier()
+        t0 = time.perf_counter()
+        r = fn()
+        torch.cuda.synchronize()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        return r, dt
+
+    ista = fm.algorithms.ISTA(A, numLambda=50.0, numMaxSteps=100)
+    fpar.solve_sharded(fm.algorithms.ISTA(A, numLambda=50.0, numMaxSteps=2), b) if distributed else ista.process(b, numMaxSteps=2)
+    ista.numMaxSteps = 100
+    res, dt = wall(lambda: (fpar.solve_sharded(ista, b) if distributed else ista.process(b)))
+    top = torch.topk(res.abs(), k, dim=0).indices
+    hit = float(((xd != 0).gather(0, top)).double().mean().item())
+    out['ista_100_steps'] = {'seconds': dt, 'columns_per_s': L * world / dt, 'operator_applies_per_s': 200 * L * world / dt,
+                             'top_k_on_true_support': hit}
+    omp = fm.algorithms.OMP(A, numMaxSteps=k)
+    res, dt = wall(lambda: (fpar.solve_sharded(omp, b, share_step_size=False) if distributed else omp.process(b)))
+    out['omp_k32'] = {'seconds': dt, 'columns_per_s': L * world / dt,
+                      'support_exact': bool(torch.equal(res != 0, xd != 0)),
+                      'max_abs_error': float((res - xd).abs().max().item())}
+    if distributed:
+        full, dt = wall(lambda: fpar.gather_columns(res, L * world))
+        out['gather_columns_all_gather'] = {'seconds': dt, 'bytes_per_rank': int(res.numel() * res.element_size()),
+                                            'gbs_per_rank_received': res.numel() * res.element_size() * (world - 1) / dt / 1e9,
+                                            'shape': list(full.shape)}
+    return out
+
+
 # ------------------------------------------------------------------------------------------- GPU arm
 def run_ours(args):
     import numpy as np
@@ -460,6 +513,17 @@ def run_ours(args):
         rec('fourier_forward_2^16_c128_64cols', lambda: F16.forward(x16), 64, 32.0 * (1 << 16), k=20)
         del x16
 
+    # ---- BASELINE config 5: ISTA / OMP on Product(Partial(Fourier(2^18), 2^16 rows), Diag), the 1024 right-hand sides of
+    #      the 8-GPU batch sharded 128 per GPU (every rank solves its own shard: no collective inside the solvers; the
+    #      assembled result costs one all_gather, timed separately).  Runs at every N.
+    config5 = None
+    if not args.quick or distributed:
+        try:
+            config5 = run_config5(fm, fpar, dev, rank, world, distributed, barrier, max_over_ranks, args.c5_cols)
+        except Exception as e:
+            config5 = {'error': repr(e)}
+            torch.cuda.synchronize()
+
     cpu = None
     check = None
     if rank == 0 and not args.no_cpu and not distributed:          # reported at N = 1 only
@@ -500,6 +564,7 @@ def run_ours(args):
                          'kernel_source_hash': shash},
             'output_check': check,
             'cpu_baseline': cpu,
+            'config5_solvers': config5,
             'extras': extras,
         }
         print(json.dumps(line))
@@ -519,6 +584,7 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=2, dest='e2e_steps')
     ap.add_argument('--sustain', type=float, default=2.0, help='seconds of back-to-back steps for the sustained figure (0: off)')
     ap.add_argument('--cpu-cols', type=int, default=16, dest='cpu_cols')
+    ap.add_argument('--c5-cols', type=int, default=128, dest='c5_cols', help='right-hand sides per GPU of the config-5 solver rows')
     ap.add_argument('--quick', action='store_true', help='headline only (no extras)')
     ap.add_argument('--no-e2e', action='store_true', dest='no_e2e')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')

@@ -46,6 +46,10 @@ SIGNATURES = {
     'fmb_conjugate': (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp, c_i64, c_i64, c_i64, c_i64, ctypes.c_int, c_vp]),
     'fmb_ista_step': (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, ctypes.c_double, ctypes.c_double, ctypes.c_int, c_vp]),
     'fmb_cast': (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_i64, c_i64, ctypes.c_int, c_i64, c_i64, c_vp]),
+    'fmb_abs_argmax_workspace_bytes': (c_i64, [c_i64]),
+    'fmb_abs_argmax': (ctypes.c_int, [c_vp, c_i64, c_i64, c_i64, ctypes.c_int, c_vp, c_vp, c_i64, c_vp]),
+    'fmb_gs_project': (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, ctypes.c_int, c_vp]),
+    'fmb_gs_subtract': (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, c_vp, c_i64, c_i64, c_i64, c_vp, c_i64, ctypes.c_int, c_vp]),
     'fmb_launch_count': (c_i64, []),
 }
 

@@ -1,61 +1,78 @@
-"""Algorithm base class (fastmat/algorithms/Algorithm.pyx:27-175): parameter handling, callbacks, trace."""
-from copy import copy
+"""Solver base class of fastmat_b200.algorithms.
+
+Public behaviour follows fastmat/algorithms/Algorithm.pyx:27-175 (``process(arrB, **params)``, ``updateParameters``,
+``snapshot`` / ``trace``, the ``cbResult`` / ``cbTrace`` callbacks, AttributeError for unknown parameters); the mechanics are
+this package's own:
+
+* every solver class DECLARES its tunables in ``PARAMETERS`` (name -> default).  The declarations of a class and of its
+  bases are merged once per class; ``__init__`` installs the defaults and ``updateParameters`` accepts declared names and
+  attributes that already exist - anything else is a typo and raises.
+* ``snapshot()`` stores a frozen record of the solver's state (a ``types.SimpleNamespace`` with the instance attributes at
+  that moment, the trace itself excluded), so a trace is a plain list of records and holds no solver objects.
+"""
+from types import SimpleNamespace
 
 
 class Algorithm(object):
 
-    def __init__(self):
+    PARAMETERS = {'cbResult': None, 'cbTrace': None}
+
+    def __init__(self, **params):
         if type(self) is Algorithm:
             raise NotImplementedError("Algorithm baseclass cannot be instantiated.")
+        self._trace = []
+        for name, default in self.declared_parameters().items():
+            setattr(self, name, default)
+        self.updateParameters(**params)
 
-    # ---- callbacks / trace (Algorithm.pyx:48-75)
-    cbTrace = None
-    cbResult = None
-    _trace = None
+    @classmethod
+    def declared_parameters(cls):
+        """PARAMETERS of the class merged over its bases (most derived declaration wins)."""
+        merged = {}
+        for klass in reversed(cls.__mro__):
+            merged.update(getattr(klass, 'PARAMETERS', {}))
+        return merged
 
+    # ---- parameters
+    def updateParameters(self, **params):
+        declared = self.declared_parameters()
+        for name in params:
+            if name not in declared and name not in self.__dict__:
+                raise AttributeError("Attribute '%s' not defined in %s" % (name, type(self).__name__))
+        for name, value in params.items():
+            setattr(self, name, value)
+
+    # ---- trace
     @property
     def trace(self):
-        if self._trace is None:
-            self._trace = []
         return self._trace
 
     @trace.setter
-    def trace(self, value):
-        if not isinstance(value, list):
+    def trace(self, records):
+        if not isinstance(records, list):
             raise TypeError("Algorithm trace must be a list")
-        self._trace = value
+        self._trace = records
 
-    def updateParameters(self, **kwargs):
-        """Algorithm.pyx:86-108: setattr every keyword; unknown attributes raise AttributeError."""
-        if getattr(self, '_attributes', None) is None:
-            self._attributes = kwargs.copy()
-        for key, value in kwargs.items():
-            if not hasattr(self, key) and (self._attributes is not None and key not in self._attributes):
-                raise AttributeError("Attribute '%s' not defined in %s" % (key, self.__class__.__name__))
-            setattr(self, key, value)
+    def snapshot(self):
+        """Append a record of the current state to the trace (use as ``cbTrace=Algorithm.snapshot``)."""
+        state = {k: v for k, v in self.__dict__.items() if k != '_trace'}
+        self._trace.append(SimpleNamespace(**state))
 
-    def process(self, arrB, **kwargs):
-        """Algorithm.pyx:110-126."""
-        self.updateParameters(**kwargs)
-        arrResult = self._process(arrB)
-        self.handleCallback(self.cbResult)
-        return arrResult
+    # ---- running
+    def process(self, arrB, **params):
+        """Run the solver on the right-hand side(s) ``arrB`` (1-D, or 2-D with one problem per column)."""
+        self.updateParameters(**params)
+        result = self._process(arrB)
+        self._notify(self.cbResult)
+        return result
 
     def _process(self, arrB):
         raise NotImplementedError("Algorithm is not implemented yet.")
 
-    def snapshot(self):
-        """Algorithm.pyx:136-147: append a copy of the current state (without the trace) to the trace."""
-        trace, self._trace = self._trace, []
-        if trace is None:
-            trace = []
-        trace.append(copy(self))
-        self._trace = trace
+    def _notify(self, callback):
+        return callback(self) if callback is not None else None
 
-    def handleCallback(self, callback):
-        if callback is not None:
-            return callback(self)
-        return None
+    handleCallback = _notify            # name used by the reference (Algorithm.pyx:149-172)
 
 
 def _as_device_2d(arrB, matrix):

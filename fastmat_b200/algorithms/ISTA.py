@@ -1,8 +1,8 @@
 """ISTA / FISTA on device tensors (fastmat/algorithms/ISTA.py:125-167, FISTA.py:131-170).
 
-The iteration is the reference's, statement by statement; what changes is where it runs: the gradient is two applies of
-the structured operator through the C-ABI (``backward(forward(x) - b)``), and the update ``x - L*grad`` -> soft threshold
-is ONE fused CUDA kernel (``fmb_ista_step``) instead of seven numpy sweeps.  The step size needs the largest singular
+Both solvers are one proximal-gradient loop (class ISTA below); the gradient is two applies of the structured operator
+through the C-ABI (``backward(forward(y) - b)``), and the update ``y - L*grad`` -> soft threshold is ONE fused CUDA kernel
+(``fmb_ista_step``) instead of seven numpy sweeps.  The step size needs the largest singular
 value: power iteration on the device (Matrix.largestSingularValue) replaces scipy's ARPACK ``svds``
 (fastmat/Matrix.pyx:895-919).  Columns of ``arrB`` are independent problems, so a column batch shards across GPUs with no
 collective (fastmat_b200.parallel).
@@ -37,19 +37,23 @@ def ista_step(x, grad, numL, alpha, want_step=True):
 
 
 class ISTA(Algorithm):
-    """fastmat/algorithms/ISTA.py:27-167 -- min ||Ax - b||_2^2 + lambda ||x||_1 by iterative soft thresholding."""
+    """min ||Ax - b||_2^2 + lambda ||x||_1 by proximal gradient steps (what fastmat/algorithms/ISTA.py:125-167 computes).
+
+    ISTA and FISTA are ONE loop here: a proximal gradient step from the extrapolation point ``y`` followed by the momentum
+    update of ``y``; plain ISTA is the schedule with momentum 0 (``y`` is the iterate itself).  Per step: two applies of the
+    operator through the C-ABI and one fused kernel."""
+
+    PARAMETERS = {'numLambda': 0.1, 'numMaxSteps': 100, 'cbStep': None}
+    _accelerated = False                     # FISTA: Nesterov's t-sequence (fastmat/algorithms/FISTA.py:131-170)
 
     def __init__(self, fmatA, **kwargs):
         if not isinstance(fmatA, Matrix):
             raise TypeError("fmatA must be a fastmat matrix")
         self.fmatA = fmatA
-        self.numLambda = 0.1
-        self.numMaxSteps = 100
-        self.cbStep = None
-        self.updateParameters(**kwargs)
+        super(ISTA, self).__init__(**kwargs)
 
     def softThreshold(self, arrX, numAlpha):
-        """ISTA.py:113-123."""
+        """x * max(|x| - alpha, 0) / |x| (ISTA.py:113-123), one kernel."""
         return ista_step(arrX, None, 0.0, numAlpha, want_step=False)[1]
 
     def _work_dtype(self, b):
@@ -61,19 +65,29 @@ class ISTA(Algorithm):
     def _process(self, arrB):
         self.arrB, ndim, is_np = _as_device_2d(arrB, self.fmatA)
         if self.numMaxSteps <= 0:
-            raise ValueError("ISTA would like to do at least one step for you")
+            raise ValueError("%s would like to do at least one step for you" % type(self).__name__)
         A = self.fmatA
-        self.numL = 1.0 / (A.largestSingularValue ** 2)                       # ISTA.py:143
+        self.numL = 1.0 / (A.largestSingularValue ** 2)                       # step size 1 / sigma_max^2
         tt = self._work_dtype(self.arrB)
         b = self.arrB.to(tt)
         self.arrX = torch.zeros((self.arrB.shape[1], A.numCols), dtype=tt, device=b.device).t()   # column-major
+        point = self.arrX                                                     # where the gradient is taken (y)
+        self.t = 1.0
         alpha = self.numL * self.numLambda * 0.5
         for self.numStep in range(self.numMaxSteps):
-            grad = A.backward(A.forward(self.arrX) - b)                       # ISTA.py:153-155
-            self.arrStep, self.arrX = ista_step(self.arrX, grad.to(tt), self.numL, alpha)   # :153-158 fused
-            self.handleCallback(self.cbStep)
-            self.handleCallback(self.cbTrace)
-        # the unthresholded values on the support (ISTA.py:163)
+            grad = A.backward(A.forward(point) - b)
+            previous = self.arrX
+            self.arrStep, self.arrX = ista_step(point, grad.to(tt), self.numL, alpha)
+            if self._accelerated:
+                t_next = (1.0 + np.sqrt(1.0 + 4.0 * self.t ** 2)) / 2.0
+                point = self.arrX + ((self.t - 1.0) / t_next) * (self.arrX - previous)
+                self.t = t_next
+                self.arrY = point
+            else:
+                point = self.arrX
+            self._notify(self.cbStep)
+            self._notify(self.cbTrace)
+        # de-biasing as in the reference: the unthresholded step values on the support (ISTA.py:163, FISTA.py:169)
         self.arrResult = torch.where(self.arrX != 0, self.arrStep, self.arrX)
         if ndim == 1:
             self.arrResult = self.arrResult.reshape(-1)
@@ -82,31 +96,6 @@ class ISTA(Algorithm):
 
 
 class FISTA(ISTA):
-    """fastmat/algorithms/FISTA.py:28-170 -- ISTA with Nesterov momentum."""
+    """ISTA with Nesterov momentum (fastmat/algorithms/FISTA.py:28-170): the same loop, accelerated schedule."""
 
-    def _process(self, arrB):
-        self.arrB, ndim, is_np = _as_device_2d(arrB, self.fmatA)
-        if self.numMaxSteps <= 0:
-            raise ValueError("FISTA would like to do at least one step for you")
-        A = self.fmatA
-        self.numL = 1.0 / (A.largestSingularValue ** 2)
-        self.t = 1
-        tt = self._work_dtype(self.arrB)
-        b = self.arrB.to(tt)
-        self.arrX = torch.zeros((self.arrB.shape[1], A.numCols), dtype=tt, device=b.device).t()
-        self.arrY = self.arrX.clone(memory_format=torch.preserve_format)
-        alpha = self.numL * self.numLambda * 0.5
-        for self.numStep in range(self.numMaxSteps):
-            self.arrXold = self.arrX
-            grad = A.backward(A.forward(self.arrY) - b)                       # FISTA.py:152-154
-            self.arrStep, self.arrX = ista_step(self.arrY, grad.to(tt), self.numL, alpha)
-            tOld = self.t
-            self.t = (1 + np.sqrt(1 + 4 * self.t ** 2)) / 2                   # FISTA.py:160
-            self.arrY = self.arrX + ((tOld - 1) / self.t) * (self.arrX - self.arrXold)
-            self.handleCallback(self.cbStep)
-            self.handleCallback(self.cbTrace)
-        self.arrResult = torch.where(self.arrX != 0, self.arrStep, self.arrX)   # FISTA.py:169
-        if ndim == 1:
-            self.arrResult = self.arrResult.reshape(-1)
-        self.arrResult = _finish(self.arrResult, is_np)
-        return self.arrResult
+    _accelerated = True

@@ -70,6 +70,11 @@ int ista_step_apply(const void *x, const void *grad, void *step_out, void *x_out
                     cudaStream_t st);
 int cast_apply(const void *x, int64_t xrs, int64_t xcs, int dt_x, void *y, int64_t yrs, int64_t ycs, int dt_out, int64_t n, int64_t M,
                cudaStream_t st);
+int gs_step_apply(int subtract, const void *q, int64_t q_bs, int64_t q_rs, int k, void *v, int64_t v_bs, int64_t n, int64_t batches,
+                  void *coef, int64_t coef_bs, int dtype, cudaStream_t st);
+int64_t abs_argmax_workspace_bytes(int64_t cols);
+int abs_argmax_apply(const void *x, int64_t rows, int64_t cols, int64_t col_stride, int dtype, int64_t *out, void *ws, int64_t ws_bytes,
+                     cudaStream_t st);
 
 static size_t out_csize(int dt_out) { return dt_out == FMB_COMPLEX64 ? sizeof(float2) : sizeof(double2); }
 
@@ -442,6 +447,31 @@ int fmb_ista_step(const void *x, const void *grad, void *step_out, void *x_out, 
                   void *cuda_stream) {
     FMB_GUARD_BEGIN
     return ista_step_apply(x, grad, step_out, x_out, count, num_l, alpha, dtype, (cudaStream_t)cuda_stream);
+    FMB_GUARD_END
+}
+
+int64_t fmb_abs_argmax_workspace_bytes(int64_t cols) { return abs_argmax_workspace_bytes(cols); }
+
+int fmb_abs_argmax(const void *x, int64_t rows, int64_t cols, int64_t col_stride, int dtype, int64_t *out_index, void *workspace,
+                   int64_t workspace_bytes, void *cuda_stream) {
+    FMB_GUARD_BEGIN
+    return abs_argmax_apply(x, rows, cols, col_stride, dtype, out_index, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+    FMB_GUARD_END
+}
+
+int fmb_gs_project(const void *q, int64_t q_batch_stride, int64_t q_row_stride, int k, const void *v, int64_t v_batch_stride, int64_t n,
+                   int64_t batches, void *coef, int64_t coef_batch_stride, int dtype, void *cuda_stream) {
+    FMB_GUARD_BEGIN
+    return gs_step_apply(0, q, q_batch_stride, q_row_stride, k, const_cast<void *>(v), v_batch_stride, n, batches, coef, coef_batch_stride,
+                         dtype, (cudaStream_t)cuda_stream);
+    FMB_GUARD_END
+}
+
+int fmb_gs_subtract(const void *q, int64_t q_batch_stride, int64_t q_row_stride, int k, void *v, int64_t v_batch_stride, int64_t n,
+                    int64_t batches, const void *coef, int64_t coef_batch_stride, int dtype, void *cuda_stream) {
+    FMB_GUARD_BEGIN
+    return gs_step_apply(1, q, q_batch_stride, q_row_stride, k, v, v_batch_stride, n, batches, const_cast<void *>(coef), coef_batch_stride,
+                         dtype, (cudaStream_t)cuda_stream);
     FMB_GUARD_END
 }
 

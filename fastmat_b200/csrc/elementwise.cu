@@ -1,6 +1,7 @@
 // Exact element-wise pieces of the apply path: Diag multiply (fastmat/Diag.pyx:149-167 ->
 // fastmat/core/cmath.pyx:958-1012 _multiply), the Partial gather / scatter (fastmat/Partial.pyx:268-294),
 // complex conjugate (fastmat/core/cmath.pyx:744-840).  All are pure bandwidth: one read, one write.
+#include <algorithm>
 #include "common.h"
 #include "cx.cuh"
 
@@ -404,6 +405,184 @@ int ista_step_apply(const void *x, const void *grad, void *step_out, void *x_out
     }
     FMB_LAUNCH_OK();
     return FMB_OK;
+#endif
+}
+
+// ---- OMP atom selection (fastmat/algorithms/OMP.pyx:196-199: argmax(abs(C^H r)) per column) as ONE sweep: the magnitude
+// array is never materialised.  Column-major input, `chunks` CTAs per column write (value, index) partials, a second tiny
+// kernel picks the winner; ties go to the lowest index, like np.argmax.
+template <typename V> struct Mag2;
+template <> struct Mag2<float> { typedef float S; static __device__ __forceinline__ float of(float v) { return v * v; } };
+template <> struct Mag2<double> { typedef double S; static __device__ __forceinline__ double of(double v) { return v * v; } };
+template <> struct Mag2<float2> { typedef float S; static __device__ __forceinline__ float of(float2 v) { return v.x * v.x + v.y * v.y; } };
+template <> struct Mag2<double2> { typedef double S; static __device__ __forceinline__ double of(double2 v) { return v.x * v.x + v.y * v.y; } };
+constexpr int ARGMAX_CHUNKS = 8, ARGMAX_NT = 512;
+struct ArgmaxPartial { double val; long long idx; };
+
+template <typename V>
+__global__ void __launch_bounds__(ARGMAX_NT) abs_argmax_kernel(const V *__restrict__ x, long long rows, long long col_stride,
+                                                               ArgmaxPartial *__restrict__ part) {
+    typedef typename Mag2<V>::S S;
+    const long long col = blockIdx.y, per = (rows + ARGMAX_CHUNKS - 1) / ARGMAX_CHUNKS;
+    const long long r0 = blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+    const V *xc = x + col * col_stride;
+    S best = (S)-1;
+    long long bi = r0;
+    for (long long r = r0 + threadIdx.x; r < r1; r += ARGMAX_NT) {
+        const S m = Mag2<V>::of(xc[r]);
+        if (m > best) { best = m; bi = r; }               // ascending r within a thread: the first maximum is kept
+    }
+    __shared__ double sv[ARGMAX_NT];
+    __shared__ long long si[ARGMAX_NT];
+    sv[threadIdx.x] = (double)best; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = ARGMAX_NT / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            const double v2 = sv[threadIdx.x + o];
+            const long long i2 = si[threadIdx.x + o];
+            if (v2 > sv[threadIdx.x] || (v2 == sv[threadIdx.x] && i2 < si[threadIdx.x])) { sv[threadIdx.x] = v2; si[threadIdx.x] = i2; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part[col * ARGMAX_CHUNKS + blockIdx.x].val = sv[0]; part[col * ARGMAX_CHUNKS + blockIdx.x].idx = si[0]; }
+}
+__global__ void abs_argmax_final_kernel(const ArgmaxPartial *__restrict__ part, long long cols, long long *__restrict__ out) {
+    const long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= cols) return;
+    double best = -1.0;
+    long long bi = 0;
+    for (int k = 0; k < ARGMAX_CHUNKS; ++k) {             // chunks in ascending row order: strict > keeps the first maximum
+        const ArgmaxPartial p = part[c * ARGMAX_CHUNKS + k];
+        if (p.val > best) { best = p.val; bi = p.idx; }
+    }
+    out[c] = bi;
+}
+
+int64_t abs_argmax_workspace_bytes(int64_t cols) { return cols * ARGMAX_CHUNKS * (int64_t)sizeof(ArgmaxPartial); }
+
+int abs_argmax_apply(const void *x, int64_t rows, int64_t cols, int64_t col_stride, int dtype, int64_t *out, void *ws, int64_t ws_bytes,
+                     cudaStream_t st) {
+#ifdef FMB_EMULATE
+    set_error("element-wise kernels are not emulated");
+    return FMB_ERR_NOTIMPL;
+#else
+    if (rows <= 0 || cols <= 0) return FMB_OK;
+    if (ws == nullptr || ws_bytes < abs_argmax_workspace_bytes(cols)) { set_error("abs_argmax: workspace too small"); return FMB_ERR_WORKSPACE; }
+    if (cols > 65535) { set_error("abs_argmax: more than 65535 columns per call"); return FMB_ERR_VALUE; }
+    const dim3 grid(ARGMAX_CHUNKS, (unsigned)cols);
+    ArgmaxPartial *part = (ArgmaxPartial *)ws;
+    switch (dtype) {
+        case FMB_FLOAT32: abs_argmax_kernel<float><<<grid, ARGMAX_NT, 0, st>>>((const float *)x, rows, col_stride, part); break;
+        case FMB_FLOAT64: abs_argmax_kernel<double><<<grid, ARGMAX_NT, 0, st>>>((const double *)x, rows, col_stride, part); break;
+        case FMB_COMPLEX64: abs_argmax_kernel<float2><<<grid, ARGMAX_NT, 0, st>>>((const float2 *)x, rows, col_stride, part); break;
+        case FMB_COMPLEX128: abs_argmax_kernel<double2><<<grid, ARGMAX_NT, 0, st>>>((const double2 *)x, rows, col_stride, part); break;
+        default: set_error("abs_argmax: unsupported dtype %d (float32/64, complex64/128)", dtype); return FMB_ERR_TYPE;
+    }
+    FMB_LAUNCH_OK();
+    abs_argmax_final_kernel<<<(unsigned)((cols + 127) / 128), 128, 0, st>>>(part, cols, (long long *)out);
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+#endif
+}
+
+// ---- batched Gram-Schmidt step of OMP's incremental QR (fastmat_b200/algorithms/OMP.py): `batches` independent problems,
+// problem l holds k orthonormal rows Q[l, j, :] (j < k) of length n and a new vector v[l, :]:
+//      project :  coef[l, j] = sum_n conj(Q[l, j, n]) * v[l, n]
+//      subtract:  v[l, n]   -= sum_j coef[l, j] * Q[l, j, n]
+// Two memory-bound sweeps over the used part of Q per orthogonalisation (cuBLAS batched products of these skinny shapes
+// in complex128 took ~40 ms per call at k ~ 16, n = 2^16, 128 batches; these take the time of reading Q).
+template <typename V> struct GsOps;
+template <> struct GsOps<float> {
+    static __device__ __forceinline__ float cmac(float acc, float q, float v) { return acc + q * v; }       // conj(q) * v
+    static __device__ __forceinline__ float mac(float acc, float c, float q) { return acc + c * q; }
+    static __device__ __forceinline__ float zero() { return 0.f; }
+    static __device__ __forceinline__ float add(float a, float b) { return a + b; }
+    static __device__ __forceinline__ float sub(float a, float b) { return a - b; }
+};
+template <> struct GsOps<double> {
+    static __device__ __forceinline__ double cmac(double acc, double q, double v) { return acc + q * v; }
+    static __device__ __forceinline__ double mac(double acc, double c, double q) { return acc + c * q; }
+    static __device__ __forceinline__ double zero() { return 0.0; }
+    static __device__ __forceinline__ double add(double a, double b) { return a + b; }
+    static __device__ __forceinline__ double sub(double a, double b) { return a - b; }
+};
+template <> struct GsOps<float2> {
+    static __device__ __forceinline__ float2 cmac(float2 a, float2 q, float2 v) { return make_float2(a.x + q.x * v.x + q.y * v.y, a.y + q.x * v.y - q.y * v.x); }
+    static __device__ __forceinline__ float2 mac(float2 a, float2 c, float2 q) { return make_float2(a.x + c.x * q.x - c.y * q.y, a.y + c.x * q.y + c.y * q.x); }
+    static __device__ __forceinline__ float2 zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ float2 add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+    static __device__ __forceinline__ float2 sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+};
+template <> struct GsOps<double2> {
+    static __device__ __forceinline__ double2 cmac(double2 a, double2 q, double2 v) { return make_double2(a.x + q.x * v.x + q.y * v.y, a.y + q.x * v.y - q.y * v.x); }
+    static __device__ __forceinline__ double2 mac(double2 a, double2 c, double2 q) { return make_double2(a.x + c.x * q.x - c.y * q.y, a.y + c.x * q.y + c.y * q.x); }
+    static __device__ __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
+    static __device__ __forceinline__ double2 add(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+    static __device__ __forceinline__ double2 sub(double2 a, double2 b) { return make_double2(a.x - b.x, a.y - b.y); }
+};
+constexpr int GS_NT = 256, GS_MAXK = 256;
+
+template <typename V>
+__global__ void __launch_bounds__(GS_NT) gs_project_kernel(const V *__restrict__ q, long long q_bs, long long q_rs, const V *__restrict__ v,
+                                                           long long v_bs, long long n, V *__restrict__ coef, long long coef_bs) {
+    const long long l = blockIdx.y;
+    const int j = blockIdx.x;
+    const V *qr = q + l * q_bs + j * q_rs, *vr = v + l * v_bs;
+    V acc = GsOps<V>::zero();
+    for (long long e = threadIdx.x; e < n; e += GS_NT) acc = GsOps<V>::cmac(acc, qr[e], vr[e]);
+    __shared__ V red[GS_NT];
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = GS_NT / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] = GsOps<V>::add(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) coef[l * coef_bs + j] = red[0];
+}
+template <typename V>
+__global__ void __launch_bounds__(GS_NT) gs_subtract_kernel(const V *__restrict__ q, long long q_bs, long long q_rs, V *__restrict__ v,
+                                                            long long v_bs, long long n, const V *__restrict__ coef, long long coef_bs, int k) {
+    const long long l = blockIdx.y;
+    __shared__ V c[GS_MAXK];
+    for (int j = threadIdx.x; j < k; j += GS_NT) c[j] = coef[l * coef_bs + j];
+    __syncthreads();
+    const V *qb = q + l * q_bs;
+    V *vr = v + l * v_bs;
+    for (long long e = (long long)blockIdx.x * GS_NT + threadIdx.x; e < n; e += (long long)gridDim.x * GS_NT) {
+        V acc = GsOps<V>::zero();
+        for (int j = 0; j < k; ++j) acc = GsOps<V>::mac(acc, c[j], qb[j * q_rs + e]);
+        vr[e] = GsOps<V>::sub(vr[e], acc);
+    }
+}
+
+template <typename V>
+static int gs_step_t(int subtract, const void *q, int64_t q_bs, int64_t q_rs, int k, void *v, int64_t v_bs, int64_t n, int64_t batches,
+                     void *coef, int64_t coef_bs, cudaStream_t st) {
+    if (!subtract) {
+        gs_project_kernel<V><<<dim3((unsigned)k, (unsigned)batches), GS_NT, 0, st>>>((const V *)q, q_bs, q_rs, (const V *)v, v_bs, n, (V *)coef, coef_bs);
+    } else {
+        const unsigned gx = (unsigned)std::max<int64_t>(1, std::min<int64_t>((n + GS_NT - 1) / GS_NT, 64));
+        gs_subtract_kernel<V><<<dim3(gx, (unsigned)batches), GS_NT, 0, st>>>((const V *)q, q_bs, q_rs, (V *)v, v_bs, n, (const V *)coef, coef_bs, k);
+    }
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+}
+
+int gs_step_apply(int subtract, const void *q, int64_t q_bs, int64_t q_rs, int k, void *v, int64_t v_bs, int64_t n, int64_t batches,
+                  void *coef, int64_t coef_bs, int dtype, cudaStream_t st) {
+#ifdef FMB_EMULATE
+    set_error("element-wise kernels are not emulated");
+    return FMB_ERR_NOTIMPL;
+#else
+    if (k <= 0 || n <= 0 || batches <= 0) return FMB_OK;
+    if (k > GS_MAXK || batches > 65535) { set_error("gs_step: at most %d basis vectors and 65535 problems per call", GS_MAXK); return FMB_ERR_VALUE; }
+    switch (dtype) {
+        case FMB_FLOAT32: return gs_step_t<float>(subtract, q, q_bs, q_rs, k, v, v_bs, n, batches, coef, coef_bs, st);
+        case FMB_FLOAT64: return gs_step_t<double>(subtract, q, q_bs, q_rs, k, v, v_bs, n, batches, coef, coef_bs, st);
+        case FMB_COMPLEX64: return gs_step_t<float2>(subtract, q, q_bs, q_rs, k, v, v_bs, n, batches, coef, coef_bs, st);
+        case FMB_COMPLEX128: return gs_step_t<double2>(subtract, q, q_bs, q_rs, k, v, v_bs, n, batches, coef, coef_bs, st);
+        default: set_error("gs_step: unsupported dtype %d (float32/64, complex64/128)", dtype); return FMB_ERR_TYPE;
+    }
 #endif
 }
 

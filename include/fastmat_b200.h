@@ -152,6 +152,25 @@ int fmb_cast(const void *x, int64_t x_row_stride, int64_t x_col_stride, int dtyp
 int fmb_ista_step(const void *x, const void *grad, void *step_out, void *x_out, int64_t count,
                   double num_l, double alpha, int dtype, void *cuda_stream);
 
+/* Atom selection of OMP (fastmat/algorithms/OMP.pyx:196-199: np.argmax(np.abs(C^H r), axis=0)) in one sweep over a
+ * column-major (rows x cols) device array (element (r, c) at x[c * col_stride + r]): out_index[c] = the row of the largest
+ * magnitude of column c, the first one on ties (as np.argmax).  The magnitude array is never formed.  dtype: float32/64,
+ * complex64/128; cols <= 65535; workspace: fmb_abs_argmax_workspace_bytes(cols) device bytes. */
+int64_t fmb_abs_argmax_workspace_bytes(int64_t cols);
+int fmb_abs_argmax(const void *x, int64_t rows, int64_t cols, int64_t col_stride, int dtype, int64_t *out_index,
+                   void *workspace, int64_t workspace_bytes, void *cuda_stream);
+
+/* Batched Gram-Schmidt step of OMP's incremental QR (replaces the explicit pseudo-inverse updates of
+ * fastmat/algorithms/OMP.pyx:211-241): `batches` independent problems; problem l has k orthonormal rows
+ * q[l * q_batch_stride + j * q_row_stride + (0..n-1)] and a vector v[l * v_batch_stride + (0..n-1)] (element strides):
+ *     fmb_gs_project :  coef[l * coef_batch_stride + j] = sum_e conj(q[l, j, e]) * v[l, e]       (j < k)
+ *     fmb_gs_subtract:  v[l, e] -= sum_j coef[l, j] * q[l, j, e]                                 (in place)
+ * dtype: float32/64, complex64/128; k <= 256, batches <= 65535. */
+int fmb_gs_project(const void *q, int64_t q_batch_stride, int64_t q_row_stride, int k, const void *v, int64_t v_batch_stride,
+                   int64_t n, int64_t batches, void *coef, int64_t coef_batch_stride, int dtype, void *cuda_stream);
+int fmb_gs_subtract(const void *q, int64_t q_batch_stride, int64_t q_row_stride, int k, void *v, int64_t v_batch_stride,
+                    int64_t n, int64_t batches, const void *coef, int64_t coef_batch_stride, int dtype, void *cuda_stream);
+
 /* Count of kernel launches issued by this library in the calling process (for bench.py's gpu_launches). */
 int64_t fmb_launch_count(void);
 

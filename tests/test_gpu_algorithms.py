@@ -145,24 +145,71 @@ def test_config5_compressed_sensing_recovery(fm):
 
 def test_norm_and_singular_value_shortcuts(fm):
     """colNorms / rowNorms / largestSingularValue overrides (fastmat/Partial.pyx:234-250, Kron.pyx:155-183, plus the
-    exact Diag-factor shortcut of Product) against the dense reference matrix."""
+    exact Diag-factor shortcut of Product) against dense matrices assembled from the ORACLE's constructions
+    (oracle.fastmat_oracle.dense_fourier / dense_hadamard - the reference's own `_reference` recipes), not the package's."""
+    from oracle import fastmat_oracle as orc
     rng = np.random.default_rng(11)
     d = (rng.standard_normal(64) + 1j * rng.standard_normal(64)).astype(np.complex128)
     rows = np.sort(rng.choice(64, 20, replace=False))
     cols = np.sort(rng.choice(64, 33, replace=False))
-    mats = [fm.Partial(fm.Fourier(64), cols=cols), fm.Partial(fm.Hadamard(6), rows=rows),
-            fm.Partial(fm.Fourier(64), rows=rows, cols=cols), fm.Kron(fm.Fourier(8), fm.Hadamard(3)),
-            fm.Product(fm.Partial(fm.Fourier(64), rows=rows), fm.Diag(d)), fm.Product(fm.Diag(d), fm.Fourier(64)),
-            fm.Product(fm.Diag(d), fm.Partial(fm.Fourier(64), cols=cols), 2.5)]
-    for M in mats:
-        ref = M.reference().to(torch.complex128)
+    F64, H6 = orc.dense_fourier(64), orc.dense_hadamard(6).astype(np.float64)
+    cases = [(fm.Partial(fm.Fourier(64), cols=cols), F64[:, cols]),
+             (fm.Partial(fm.Hadamard(6), rows=rows), H6[rows, :]),
+             (fm.Partial(fm.Fourier(64), rows=rows, cols=cols), F64[np.ix_(rows, cols)]),
+             (fm.Kron(fm.Fourier(8), fm.Hadamard(3)), np.kron(orc.dense_fourier(8), orc.dense_hadamard(3).astype(np.float64))),
+             (fm.Product(fm.Partial(fm.Fourier(64), rows=rows), fm.Diag(d)), F64[rows, :] * d[None, :]),
+             (fm.Product(fm.Diag(d), fm.Fourier(64)), d[:, None] * F64),
+             (fm.Product(fm.Diag(d), fm.Partial(fm.Fourier(64), cols=cols), 2.5), 2.5 * d[:, None] * F64[:, cols])]
+    for M, ref in cases:
         assert ref.shape == (M.numRows, M.numCols)
-        cn = torch.linalg.vector_norm(ref, dim=0)
-        rn = torch.linalg.vector_norm(ref, dim=1)
-        assert float((M.colNorms.to(torch.float64) - cn).abs().max()) <= 1e-9 * float(cn.max()), repr(M)
-        assert float((M.rowNorms.to(torch.float64) - rn).abs().max()) <= 1e-9 * float(rn.max()), repr(M)
-        s = float(torch.linalg.matrix_norm(ref, ord=2))
-        assert abs(M.largestSingularValue - s) <= 1e-8 * s, repr(M)
+        # the package's own dense construction agrees with the oracle's, too
+        assert np.abs(M.reference().cpu().numpy() - ref).max() <= 1e-9 * np.abs(ref).max(), repr(M)
+        cn, rn = np.linalg.norm(ref, axis=0), np.linalg.norm(ref, axis=1)
+        assert np.abs(M.colNorms.cpu().numpy().astype(np.float64) - cn).max() <= 1e-9 * cn.max(), repr(M)
+        assert np.abs(M.rowNorms.cpu().numpy().astype(np.float64) - rn).max() <= 1e-9 * rn.max(), repr(M)
+        s_ref = np.linalg.norm(ref, ord=2)
+        assert abs(M.largestSingularValue - s_ref) <= 1e-8 * s_ref, repr(M)
+
+
+def test_abs_argmax_kernel_matches_numpy(fm):
+    """fmb_abs_argmax (OMP's atom selection in one sweep) == np.argmax(np.abs(x), axis=0), first maximum on ties, for every
+    dtype, ragged row counts (chunk boundaries) and strided column batches."""
+    from fastmat_b200.algorithms.OMP import abs_argmax
+    rng = np.random.default_rng(21)
+    for dt in (np.float32, np.float64, np.complex64, np.complex128):
+        for rows, cols in ((1, 3), (7, 5), (4099, 17), (65536, 9)):
+            x = rng.standard_normal((rows, cols))
+            if np.dtype(dt).kind == 'c':
+                x = x + 1j * rng.standard_normal((rows, cols))
+            x = x.astype(dt)
+            if rows > 8:                                             # exact ties: the first one must win
+                x[5, 0] = x[rows - 3, 0] = 100.0
+                x[rows // 2, 1] = x[rows // 2 + 1, 1] = -50.0
+            got = abs_argmax(colmajor(x)).cpu().numpy()
+            assert np.array_equal(got, np.argmax(np.abs(x), axis=0)), (dt, rows, cols)
+    wide = colmajor(rng.standard_normal((300, 12)).astype(np.float32))
+    assert np.array_equal(abs_argmax(wide[:, 2:9]).cpu().numpy(), np.argmax(np.abs(wide.cpu().numpy()[:, 2:9]), axis=0))
+
+
+def test_algorithm_base_parameters_trace_and_callbacks(fm):
+    """Behaviour of fastmat/algorithms/Algorithm.pyx the solvers inherit: declared defaults, AttributeError for unknown
+    parameters (at construction and at process()), per-step callbacks, snapshot() records in .trace, cbResult once."""
+    A = build(fm, 'cs', np.complex128)
+    alg = fm.algorithms.ISTA(A)
+    assert (alg.numLambda, alg.numMaxSteps, alg.cbStep, alg.cbTrace, alg.cbResult) == (0.1, 100, None, None, None)
+    with pytest.raises(AttributeError):
+        fm.algorithms.OMP(A, numLamda=3)
+    with pytest.raises(NotImplementedError):
+        fm.algorithms.Algorithm()
+    with pytest.raises(TypeError):
+        alg.trace = 'not a list'
+    seen, done = [], []
+    alg = fm.algorithms.FISTA(A, numMaxSteps=5, cbStep=lambda a: seen.append(a.numStep), cbTrace=fm.algorithms.Algorithm.snapshot,
+                              cbResult=lambda a: done.append(a.numStep))
+    alg.process(colmajor(GA['cs_b']), numLambda=0.25)
+    assert seen == [0, 1, 2, 3, 4] and done == [4] and alg.numLambda == 0.25
+    assert [r.numStep for r in alg.trace] == [0, 1, 2, 3, 4] and not hasattr(alg.trace[0], '_trace')
+    assert alg.trace[1].arrX is not alg.trace[3].arrX                # records keep the state of THEIR step
 
 
 @pytest.mark.parametrize('tag', ['cs', 'had'])
