@@ -586,4 +586,50 @@ int gs_step_apply(int subtract, const void *q, int64_t q_bs, int64_t q_rs, int k
 #endif
 }
 
+// ---- out[j * ldb + i] = in[i * lda + j], i < ni, j < nj (32 x 32 tiles through shared memory, both sides coalesced).
+// The FFT engine uses it to bring a chunk of a row-major (batch-contiguous, torch default) operand into the column-major
+// layout its fast paths work on, and the result back (fft_engine.cu: run_t).
+template <typename V>
+__global__ void __launch_bounds__(256) transpose_kernel(const V *__restrict__ in, long long lda, V *__restrict__ out, long long ldb,
+                                                        long long ni, long long nj) {
+    __shared__ V tile[32][33];
+    const long long i0 = (long long)blockIdx.y * 32, j0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (i0 + r < ni && j0 + tx < nj) tile[r][tx] = in[(i0 + r) * lda + j0 + tx];
+    __syncthreads();
+#pragma unroll
+    for (int r = ty; r < 32; r += 8)
+        if (j0 + r < nj && i0 + tx < ni) out[(j0 + r) * ldb + i0 + tx] = tile[tx][r];
+}
+
+int transpose_apply(const void *in, int64_t lda, void *out, int64_t ldb, int64_t ni, int64_t nj, size_t esize, cudaStream_t st) {
+#ifdef FMB_EMULATE
+    set_error("element-wise kernels are not emulated");
+    return FMB_ERR_NOTIMPL;
+#else
+    if (ni <= 0 || nj <= 0) return FMB_OK;
+    const long long gy = (ni + 31) / 32, gx = (nj + 31) / 32;
+    if (gy > 65535) {
+        // rows are the long dimension: put them on grid.x by swapping the roles of the block indices is not possible with a
+        // fixed kernel, so walk the rows in slices of 65535 tiles
+        for (long long t0 = 0; t0 < gy; t0 += 65535) {
+            const long long nt = std::min<long long>(65535, gy - t0), r0 = t0 * 32, nr = std::min<long long>(nt * 32, ni - r0);
+            const dim3 grid((unsigned)gx, (unsigned)nt);
+            if (esize == 8) transpose_kernel<float2><<<grid, 256, 0, st>>>((const float2 *)in + r0 * lda, lda, (float2 *)out + r0, ldb, nr, nj);
+            else transpose_kernel<double2><<<grid, 256, 0, st>>>((const double2 *)in + r0 * lda, lda, (double2 *)out + r0, ldb, nr, nj);
+            FMB_LAUNCH_OK();
+        }
+        return FMB_OK;
+    }
+    const dim3 grid((unsigned)gx, (unsigned)gy);
+    if (esize == 8) transpose_kernel<float2><<<grid, 256, 0, st>>>((const float2 *)in, lda, (float2 *)out, ldb, ni, nj);
+    else if (esize == 16) transpose_kernel<double2><<<grid, 256, 0, st>>>((const double2 *)in, lda, (double2 *)out, ldb, ni, nj);
+    else { set_error("transpose: element size %d", (int)esize); return FMB_ERR_TYPE; }
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+#endif
+}
+
 }  // namespace fmb

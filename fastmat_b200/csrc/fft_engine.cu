@@ -267,7 +267,22 @@ int ConvEngine::slab_cols(int64_t M, size_t csize) const {
     return cols;
 }
 
+int transpose_apply(const void *in, int64_t lda, void *out, int64_t ldb, int64_t ni, int64_t nj, size_t esize, cudaStream_t st);
+static int64_t rm_chunk() {
+    static const long v = env_long("FMB_RM_CHUNK", 32);
+    return v;
+}
+
+// scratch of an apply: the column-major requirement, or - if larger - what the chunked row-major route needs (a chunk's
+// column-major scratch plus its transposed input and output); the layout is not known when the caller asks
 int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
+    const int64_t cm = workspace_bytes_cm(M, csize);
+    if (shape.npass != 2 || !shape.pow2 || rm_chunk() <= 0 || M < 2) return cm;
+    const int64_t tc = std::min<int64_t>(M, rm_chunk());
+    return std::max(cm, workspace_bytes_cm(tc, csize) + (n_in + n_out) * tc * (int64_t)csize);
+}
+
+int64_t ConvEngine::workspace_bytes_cm(int64_t M, size_t csize) const {
     if (shape.npass == 1) return 0;
     const int64_t generic = (int64_t)slab_cols(M, csize) * L * (int64_t)csize;
     if (shape.pow2) {
@@ -650,6 +665,10 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
             if (!two_ffts) opt = bwd ? V32_A_FC : V32_A_F;
             else if (pre_d) opt = bwd ? V32_A_MPC : V32_A_MP;
             else opt = (rows_in < L) ? V32_A_M : V32_A_F;
+            // zero padding to exactly twice the length (Toeplitz n = m = L/2): the padded half is never loaded and the first
+            // radix-2 level of the butterflies is skipped (FMB_V32_PRUNE=0: masked loads, full butterflies)
+            static const bool prune = env_long("FMB_V32_PRUNE", 1) != 0;
+            if (prune && two_ffts && !pre_d && rows_in * 2 == L) opt = V32_A_H;
             if ((rc = launch_v32(opt, a, tiles, st))) return rc;
         }
         if (!two_ffts) {
@@ -678,6 +697,8 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
                 a.post = post_d;
                 a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[1].p;
                 unsigned opt = post_d ? (bwd ? V32_C_MPC : V32_C_MP) : (rows_out == L ? V32_C_N : V32_C_M);
+                static const bool prune = env_long("FMB_V32_PRUNE", 1) != 0;
+                if (prune && !post_d && rows_out * 2 == L) opt = V32_C_H;      // the dropped half of the rows is never computed
                 if (tw_in_c) opt |= V32_C_TW;
                 if ((rc = launch_v32(opt, a, tiles, st))) return rc;
             }
@@ -892,11 +913,29 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
         return launch_pass<C>(p, shape.g[0], pow2, rowmajor, rowmajor, rowmajor, st);
     }
 
+    // ---------------- row-major (batch-contiguous, torch's default) operands of the power-of-two two-pass shapes: chunks of
+    // FMB_RM_CHUNK columns are transposed into the column-major layout, pushed through the fast path and transposed back
+    // (the generic strided kernel below needs 5-9x the time of the fast path; two extra sweeps cost ~0.7x).
+    if (rowmajor && ycs == 1 && !in_real && fast_ok<C>(1, 1, false) && rm_chunk() > 0) {
+        const int64_t tc = std::min<int64_t>(M, rm_chunk());
+        const int64_t inner = workspace_bytes_cm(tc, sizeof(C));
+        const int64_t need = inner + (rows_in + rows_out) * tc * (int64_t)sizeof(C);
+        if (ws == nullptr || ws_bytes < need) { set_error("workspace too small: need %lld bytes", (long long)need); return FMB_ERR_WORKSPACE; }
+        C *xt = (C *)((char *)ws + inner), *yt = xt + rows_in * tc;
+        for (int64_t c0 = 0; c0 < M; c0 += tc) {
+            const int64_t nc = std::min(tc, M - c0);
+            if ((rc = transpose_apply((const C *)x + c0, xrs, xt, rows_in, rows_in, nc, sizeof(C), st))) return rc;
+            if ((rc = run_t<C>(d, direction, xt, 1, rows_in, false, yt, 1, rows_out, nc, ws, inner, st))) return rc;
+            if ((rc = transpose_apply(yt, rows_out, (C *)y + c0, yrs, nc, rows_out, sizeof(C), st))) return rc;
+        }
+        return FMB_OK;
+    }
+
     // ---------------- two shared-memory passes per transform, slab by slab over an L2-resident intermediate
     const int64_t slab = slab_cols(M, sizeof(C));
     if (fast_ok<C>(xrs, yrs, in_real)) {
-        if (ws == nullptr || ws_bytes < workspace_bytes(M, sizeof(C))) {
-            set_error("workspace too small: need %lld bytes", (long long)workspace_bytes(M, sizeof(C)));
+        if (ws == nullptr || ws_bytes < workspace_bytes_cm(M, sizeof(C))) {
+            set_error("workspace too small: need %lld bytes", (long long)workspace_bytes_cm(M, sizeof(C)));
             return FMB_ERR_WORKSPACE;
         }
         if (v32_ok(sizeof(C)) && v32p_ok(direction, x, xcs, y, ycs)) return run_v32p(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);

@@ -52,6 +52,7 @@ struct ConvEngine {
     int slab_cols(int64_t M, size_t csize) const;
     void slab_plan(int64_t M, size_t csize, bool fast, int &cols, int &ns) const;
     int64_t workspace_bytes(int64_t M, size_t csize) const;
+    int64_t workspace_bytes_cm(int64_t M, size_t csize) const;      // column-major operands only
     int passes() const { return shape.npass == 1 ? 1 : (two_ffts ? 3 : 2); }
 
     // dt_in: FMB_FLOAT32/64 (real input) or FMB_COMPLEX64/128; dt_out: FMB_COMPLEX64/128 (same precision as dt_in)

@@ -77,6 +77,8 @@ enum : unsigned {
     FO_PRE = 512u, FO_PRE_CONJ = 1024u,
     FO_POST = 2048u, FO_POST_CONJ = 4096u,
     FO_IN_CG = 8192u,      // the input was written by other SMs in this launch (read through L2 only)
+    FO_IN_HALF = 32768u,     // V32 passes: rows >= L/2 of the input are zero padding (Toeplitz): inputs m >= 16 of a thread are not loaded
+    FO_OUT_HALF = 65536u,    // V32 passes: only rows < L/2 of the output are kept: outputs q >= 16 of a thread are not computed
     FO_IN_TWIDDLE = 16384u,  // V32 passes: multiply the INPUT by W_N^{i f} (the four-step twiddle moved out of the previous pass)
 };
 

@@ -76,6 +76,42 @@ template <typename C> __device__ __forceinline__ void dft32(C (&v)[32]) {
     dft32_combine<C, 0>(v, e, o);
 }
 
+// dft32 of 32 inputs whose upper half (m >= 16) is zero (zero padding of a Toeplitz / linear convolution to twice the
+// length): decimation in frequency skips the first radix-2 level - even outputs are the 16-point DFT of the inputs, odd
+// outputs the 16-point DFT of the inputs times W32^m.  Natural order in and out, like dft32.
+template <typename C, int M> __device__ __forceinline__ void dft32_uz_prep(const C (&v)[32], C (&e)[16], C (&o)[16]) {
+    if constexpr (M < 16) {
+        e[M] = v[M];
+        o[M] = mul_w32<M>(v[M]);
+        dft32_uz_prep<C, M + 1>(v, e, o);
+    }
+}
+template <typename C> __device__ __forceinline__ void dft32_upper_zero(C (&v)[32]) {
+    C e[16], o[16];
+    dft32_uz_prep<C, 0>(v, e, o);
+    dft16(e);
+    dft16(o);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { v[2 * r] = e[outpos<16>(r)]; v[2 * r + 1] = o[outpos<16>(r)]; }
+}
+// dft32 whose outputs q >= 16 are not needed (the rows a Toeplitz / linear convolution discards): the radix-2 combine
+// produces only E[k] + W32^k O[k].
+template <typename C, int K> __device__ __forceinline__ void dft32_combine_lower(C (&v)[32], const C (&e)[16], const C (&o)[16]) {
+    if constexpr (K < 16) {
+        constexpr int p = outpos<16>(K);
+        v[K] = cadd(e[p], mul_w32<K>(o[p]));
+        dft32_combine_lower<C, K + 1>(v, e, o);
+    }
+}
+template <typename C> __device__ __forceinline__ void dft32_lower_only(C (&v)[32]) {
+    C e[16], o[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { e[r] = v[2 * r]; o[r] = v[2 * r + 1]; }
+    dft16(e);
+    dft16(o);
+    dft32_combine_lower<C, 0>(v, e, o);
+}
+
 // stage-twiddle pair load that is neither merged with the identical load of the pass's other transform nor hoisted as a
 // block (the compiler would otherwise keep all sixteen pairs - 64 registers - alive across the whole middle pass)
 __device__ __forceinline__ CPair<float2> ldg_pair_ordered(const CPair<float2> *p) {
@@ -160,6 +196,7 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
     constexpr bool LOAD_T = (OPT & FO_LOAD_T) != 0, STORE_T = (OPT & FO_STORE_T) != 0, TWO = (OPT & FO_TWO_FFTS) != 0;
     static_assert(LOGT == V32_LOGT || (!LOAD_T && !STORE_T), "strided sides need the 8-line tile (64-byte segments)");
     const int tid = threadIdx.x;
+    // (one tile per CTA: two or four tiles per CTA, to halve the CTA launches and keep the L1 warm, measured 25 - 55 % slower)
     const unsigned line0 = blockIdx.x << LOGT;
     const unsigned col = line0 >> 10;                      // the tile width divides 1024: a tile never straddles two columns
     const unsigned i0 = line0 & 1023u;
@@ -195,6 +232,7 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
 #pragma unroll
         for (int m = 0; m < 32; ++m) {
             const int f = jb + 32 * m;
+            if ((OPT & FO_IN_HALF) && m >= 16) { v[m] = mk<C>(0, 0); continue; }
             bool ok = true;
             if (OPT & FO_IN_MASK) ok = 32 * m < flim;
             C val = mk<C>(0, 0);
@@ -226,7 +264,8 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
 #ifdef V32_TIMING
     V32_T_MARK(v[0].x + v[31].y + v[16].x + v[15].y);                   // (most) loads have arrived, input-side multiplies done
 #endif
-    dft32(v);
+    if constexpr ((OPT & FO_IN_HALF) != 0) dft32_upper_zero(v);
+    else dft32(v);
     V32_T_MARK(v[0].x + v[31].y);                                       // first butterfly done
     auto exchange_store = [&](int jb_, int t_) {
         C *sl = smem + t_ * V32_RS + jb_ * 33;                          // position k = 32 jb + q at k + (k >> 5)
@@ -251,7 +290,8 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
             if (p2 > 0) v[2 * p2] = cmul(v[2 * p2], w.a);
             v[2 * p2 + 1] = cmul(v[2 * p2 + 1], w.b);
         }
-        dft32(v);
+        if constexpr ((OPT & FO_OUT_HALF) != 0 && !TWO) dft32_lower_only(v);
+        else dft32(v);
     };
 
     // last stage output -> global: four-step twiddle W^{i k}, conj, mask, post-multiply
@@ -267,7 +307,7 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
             klim = (room > 0 ? (room + a.out_lk - 1) / a.out_lk : 0) - jb_;
         }
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
+        for (int q = 0; q < ((OPT & FO_OUT_HALF) ? 16 : 32); ++q) {
             C val = v[q];
             if (OPT & FO_TWIDDLE) {
                 val = cmul(val, hst.c[q & 3]);
@@ -367,6 +407,8 @@ constexpr unsigned V32_C_N = FO_LOAD_T | FO_STORE_T | FO_OUT_CONJ;              
 constexpr unsigned V32_C_MP = V32_C_M | FO_POST;
 constexpr unsigned V32_C_MPC = V32_C_MP | FO_POST_CONJ;
 constexpr unsigned V32_C_TW = FO_IN_TWIDDLE;                                     // or-ed to V32_C_*: four-step twiddle on the loads
+constexpr unsigned V32_A_H = V32_A_F | FO_IN_HALF;                               // Toeplitz with n = m = L/2: rows >= L/2 are padding ...
+constexpr unsigned V32_C_H = V32_C_N | FO_OUT_HALF;                              // ... and rows >= L/2 of the result are dropped
 constexpr unsigned V32_K_A = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK;               // Kron: over i1 (stride), natural order out
 constexpr unsigned V32_K_AC = V32_K_A | FO_IN_CONJ;
 constexpr unsigned V32_K_B = FO_OUT_MASK;                                        // Kron: over i2 (contiguous)
@@ -434,8 +476,9 @@ template <unsigned OPT> int launch_v32_variant(const FastArgs<float2> &a, unsign
             case 3: return launch_v32_inst<OPT, 2, 5>(a, lines, st);
             case 4: return launch_v32_inst<OPT, 2, 6>(a, lines, st);
 #endif
-            default: return launch_v32_inst<OPT, 3, 2>(a, lines, st);
+            default: break;
         }
+        return launch_v32_inst<OPT, 3, 2>(a, lines, st);
     } else {
 #ifndef V32_LEAN
         if (shape == 1) return launch_v32_inst<OPT, 3, 3>(a, lines, st);

@@ -9,6 +9,7 @@ int launch_v32_a(unsigned opt, const FastArgs<float2> &a, unsigned lines, int sh
         case V32_A_M: return launch_v32_variant<V32_A_M>(a, lines, shape, st);
         case V32_A_MP: return launch_v32_variant<V32_A_MP>(a, lines, shape, st);
         case V32_A_MPC: return launch_v32_variant<V32_A_MPC>(a, lines, shape, st);
+        case V32_A_H: return launch_v32_variant<V32_A_H>(a, lines, shape, st);
         default: return FMB_ERR_NOTIMPL;
     }
 }

@@ -12,6 +12,8 @@ int launch_v32_c(unsigned opt, const FastArgs<float2> &a, unsigned lines, int sh
         case (V32_C_MP | V32_C_TW): return launch_v32_variant<(V32_C_MP | V32_C_TW)>(a, lines, shape, st);
         case (V32_C_MPC | V32_C_TW): return launch_v32_variant<(V32_C_MPC | V32_C_TW)>(a, lines, shape, st);
         case (V32_C_N | V32_C_TW): return launch_v32_variant<(V32_C_N | V32_C_TW)>(a, lines, shape, st);
+        case V32_C_H: return launch_v32_variant<V32_C_H>(a, lines, shape, st);
+        case (V32_C_H | V32_C_TW): return launch_v32_variant<(V32_C_H | V32_C_TW)>(a, lines, shape, st);
         default: return FMB_ERR_NOTIMPL;
     }
 }

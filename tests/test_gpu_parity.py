@@ -672,6 +672,7 @@ def test_v32p_persistent_tma_pipeline_bit_identical_to_per_pass_kernels(fm, tmp_
         # same arithmetic on both sides: the per-pass convolution applies the inverse transform's four-step twiddle on the
         # last pass's loads by default, the persistent kernel on the middle pass's stores (= FMB_V32_TWM=1)
         e['FMB_V32_TWM'] = '1'
+        e['FMB_V32_PRUNE'] = '0'                 # ... and the persistent kernel runs the full butterflies on zero-padded halves
         r = subprocess.run([sys.executable, '-c', _V32P_DUMP, path], cwd=ROOT, env=e, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout + r.stderr
         outs[mode] = torch.load(path)
