@@ -169,6 +169,7 @@ class Matrix(object):
         self._numRows = int(numRows)
         self._numCols = int(numCols)
         self._fusedType = _t.getFusedType(dataType)
+        self._device_index = torch.cuda.current_device() if torch.cuda.is_available() else None
         self._forceContiguousInput = options.get('forceContiguousInput', False)
         self._widenInputDatatype = options.get('widenInputDatatype', False)
         self._fortranStyle = options.get('fortranStyle', True)
@@ -224,6 +225,10 @@ class Matrix(object):
             raise ValueError("Input data array must be 1D or 2D")
         if x.shape[0] != required:
             raise ValueError("Mismatch of vector size %d to relevant matrix axis %d" % (x.shape[0], required))
+        home = getattr(self, '_device_index', None)
+        if home is not None and x.device.index != home:
+            # plans (device constants, per-device function attributes) belong to the device that was current at construction
+            raise RuntimeError("Input tensor lives on cuda:%d but this matrix was created on cuda:%d" % (x.device.index, home))
         ndim = x.ndim
         if x.is_complex() and x.is_conj():
             x = x.resolve_conj()
@@ -561,6 +566,54 @@ class Matrix(object):
             betas.append(beta)
             q = w / beta
         return float(np.sqrt(max(theta, 0.0)))
+
+    @property
+    def largestEigenValue(self):
+        """Largest-magnitude eigenvalue of a square matrix by power iteration on the device, Rayleigh quotient as the
+        estimate (what fastmat/Matrix.pyx:678-760 computes with numpy; every step is one forward apply through the C-ABI).
+        Cached like the reference's property."""
+        if 'lev' not in self._cache:
+            self._cache['lev'] = self._getLargestEigenValue()
+        return self._cache['lev']
+
+    def _getLargestEigenValue(self, maxSteps=10000, relEps=1e-12):
+        if self.numRows != self.numCols:
+            raise ValueError("largestEigenValue: Matrix must be square.")
+        dev = self._default_device()
+        tt = _t.getTorchType(_t.promoteTypes(self._fusedType, _t.TYPE_FLOAT64))
+        g = torch.Generator(device=dev)
+        g.manual_seed(4321)
+        v = torch.randn(self.numCols, dtype=torch.float64, device=dev, generator=g).to(tt)
+        v = v / torch.linalg.vector_norm(v)
+        lam = 0.0
+        for step in range(maxSteps):
+            w = self.forward(v).to(tt)
+            new = torch.vdot(v, w)                                       # Rayleigh quotient (||v|| = 1)
+            nrm = float(torch.linalg.vector_norm(w))
+            if nrm == 0.0:
+                return 0.0
+            v = w / nrm
+            if step % 8 == 7:                                            # one host read-back every eight steps
+                cur = complex(new.item()) if tt.is_complex else float(new.item())
+                if abs(cur - lam) <= relEps * abs(cur):
+                    lam = cur
+                    break
+                lam = cur
+        else:
+            lam = complex(new.item()) if tt.is_complex else float(new.item())
+        return lam.real if isinstance(lam, complex) and abs(lam.imag) <= 1e-12 * abs(lam) else lam
+
+    @property
+    def scipyLinearOperator(self):
+        """scipy.sparse.linalg.LinearOperator over this matrix for host (numpy) vectors, as fastmat/Matrix.pyx:977-1006:
+        matvec / matmat = forward, rmatvec / rmatmat = backward; host arrays are streamed through the device by
+        apply_host."""
+        from scipy.sparse.linalg import LinearOperator
+        return LinearOperator(shape=self.shape, dtype=self.dtype,
+                              matvec=lambda x: self.apply_host(np.asarray(x).reshape(-1)),
+                              rmatvec=lambda x: self.apply_host(np.asarray(x).reshape(-1), backward=True),
+                              matmat=lambda x: self.apply_host(np.asarray(x)),
+                              rmatmat=lambda x: self.apply_host(np.asarray(x), backward=True))
 
     def reference(self):
         """Dense reference of the matrix, built without the fast transform where a class overrides _reference."""

@@ -123,6 +123,36 @@ class Toeplitz(Matrix):
             cols &= mod < int(self._arrDimCols[i]) * below
         return Partial(P, rows=rows, cols=cols)
 
+    # ---- norms in closed form (what fastmat/Toeplitz.pyx:371-625 obtains by its level recursion): column j of one level
+    # holds the generator entries with offsets -j .. nr-1-j, so its squared norm is a difference of cumulative sums of
+    # |t|^2; for several levels the same sum runs over the squared norms of the sub-blocks.  O(size of the generator) on the
+    # host instead of numCols / chunk forward applies of one-hot slabs (16384 of them at 2^19 x 2^19).
+    def _norms2(self, t, level, rows):
+        nr, nc = int(self._arrDimRows[level]), int(self._arrDimCols[level])
+        d = nr + nc - 1
+        if t.ndim == 1:
+            P = np.abs(t.astype(np.complex128)) ** 2
+        else:
+            P = np.stack([self._norms2(t[k], level + 1, rows) for k in range(d)])
+        if rows:
+            nr, nc = nc, nr                                        # row i of T = column i of T^T: generator index reflected
+            P = np.concatenate((P[:1], P[:0:-1]), axis=0)
+        tail = P.shape[1:]
+        zero = np.zeros((1, ) + tail)
+        down = np.concatenate((zero, np.cumsum(P[:nr], axis=0)), axis=0)            # down[k] = sum of P[0 .. k-1]
+        up = np.concatenate((zero, np.cumsum(P[:nr - 1:-1] if nc > 1 else P[:0], axis=0)), axis=0)   # up[j] = sum_{q=1..j} P[d-q]
+        j = np.arange(nc)
+        # offsets 0 .. nr-1-j come from the column part, offsets -q with max(1, j-nr+1) <= q <= j from the row part
+        return down[np.clip(nr - j, 0, nr)] + up[j] - up[np.clip(j - nr, 0, None)]
+
+    def _getColNorms(self):
+        n2 = self._norms2(self._tenT, 0, False).reshape(-1)
+        return torch.from_numpy(np.sqrt(n2)).to(self._default_device())
+
+    def _getRowNorms(self):
+        n2 = self._norms2(self._tenT, 0, True).reshape(-1)
+        return torch.from_numpy(np.sqrt(n2)).to(self._default_device())
+
     def _apply(self, direction, x):
         if self._nested is not None:
             return self._nested.forward(x) if direction == FORWARD else self._nested.backward(x)

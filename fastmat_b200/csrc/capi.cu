@@ -1,4 +1,5 @@
 // extern "C" surface of libfastmat_b200.so (declared in include/fastmat_b200.h) and the plan objects behind it.
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -243,6 +244,7 @@ struct DiagPlan : PlanBase {
 
 struct PartialPlan : PlanBase {
     DevArray idx;
+    DevArray sidx;           // scatter targets without an inverse table: idx with all but the last occurrence of a value set to -1
     DevArray inv;            // inverse index (ntotal entries, -1 = row not selected), absent for very sparse selections
     int64_t nsel = 0, ntotal = 0;
     int info(fmb_plan_info *o) const override {
@@ -255,7 +257,7 @@ struct PartialPlan : PlanBase {
         if (dt_in != dt_out) { set_error("Partial: gather/scatter does not convert dtypes"); return FMB_ERR_TYPE; }
         if (direction == FMB_FORWARD) return gather_apply(idx.p, nsel, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);
         if (inv.p) return scatter_inverse_apply(inv.p, ntotal, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);
-        return scatter_apply(idx.p, nsel, ntotal, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);
+        return scatter_apply(sidx.p ? sidx.p : idx.p, nsel, ntotal, x, xrs, xcs, y, yrs, ycs, M, dt_in, st);
     }
 };
 
@@ -386,6 +388,15 @@ int fmb_partial_plan_create(fmb_plan **out, const int64_t *idx_host, int64_t num
         std::vector<int64_t> inv((size_t)num_total, (int64_t)-1);
         for (int64_t i = 0; i < num_sel; ++i) inv[(size_t)idx_host[i]] = i;
         if ((rc = p->inv.upload(inv.data(), (size_t)num_total * sizeof(int64_t)))) return rc;
+    } else if (num_sel > 0) {
+        // zero + scatter path: keep only the LAST occurrence of a repeated index (numpy semantics, deterministic)
+        std::vector<int64_t> order((size_t)num_sel), sidx(idx_host, idx_host + num_sel);
+        for (int64_t i = 0; i < num_sel; ++i) order[(size_t)i] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return idx_host[a] < idx_host[b]; });
+        bool repeats = false;
+        for (int64_t k = 0; k + 1 < num_sel; ++k)
+            if (idx_host[order[(size_t)k]] == idx_host[order[(size_t)k + 1]]) { sidx[(size_t)order[(size_t)k]] = -1; repeats = true; }
+        if (repeats && (rc = p->sidx.upload(sidx.data(), (size_t)num_sel * sizeof(int64_t)))) return rc;
     }
     *out = reinterpret_cast<fmb_plan *>(static_cast<PlanBase *>(p.release()));
     return FMB_OK;

@@ -22,6 +22,8 @@ typedef std::complex<double> cd;
 
 void set_error(const char *fmt, ...);
 extern std::atomic<long long> g_launches;
+// internal status (never leaves the library): "this path cannot run here, take the next one"
+constexpr int FMB_ERR_FALLBACK = -100;
 
 #define FMB_CUDA_OK(expr)                                                                         \
     do {                                                                                          \

@@ -109,7 +109,10 @@ template <typename B> __global__ void __launch_bounds__(256) scatter_kernel(cons
     for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
         long long r, c;
         ew_decode(p, e, r, c);
-        ((B *)p.y)[__ldg(idx + r) * p.yrs + c * p.ycs] = ((const B *)p.x)[r * p.xrs + c * p.xcs];
+        const long long target = __ldg(idx + r);
+        // a negative target marks a source row that a LATER source row overwrites (repeated index: the last occurrence
+        // wins, as in numpy's y[idx] = x; the plan removes the earlier ones on the host so that nothing races here)
+        if (target >= 0) ((B *)p.y)[target * p.yrs + c * p.ycs] = ((const B *)p.x)[r * p.xrs + c * p.xcs];
     }
 }
 
@@ -194,6 +197,7 @@ template <typename B, bool SCATTER, int CB> __global__ void __launch_bounds__(25
     const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= p.n) return;
     const long long i = __ldg((const long long *)p.d + r);
+    if (SCATTER && i < 0) return;                     // a source row that a later one overwrites (repeated index, last wins)
     const bool hole = !SCATTER && i < 0;              // inverse index of a scatter: rows nothing is written to are zero
     const B *src = (const B *)p.x + (SCATTER ? r : (hole ? 0 : i)) * p.xrs;
     B *dst = (B *)p.y + (SCATTER ? i : r) * p.yrs;

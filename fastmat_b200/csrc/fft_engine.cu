@@ -590,6 +590,10 @@ static int launch_v32(unsigned opt, const FastArgs<float2> &a, unsigned lines, c
     return rc;
 }
 
+int launch_v32t(unsigned opt, const FastArgs<float2> &a, const CUtensorMap &map, int map_col0, unsigned lines, cudaStream_t st);
+static int v32p_tensor_map(CUtensorMap *map, const void *base, int64_t rows, int64_t col_stride, int64_t cols);
+static bool v32p_tma_available();
+
 bool ConvEngine::v32_ok(size_t csize) const {
 #ifdef FMB_EMULATE
     return false;
@@ -618,15 +622,52 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
     slab_plan(M, sizeof(C), true, slab_i, ns);
     const int64_t slab = slab_i;
     int rc;
+    // FMB_V32T: the strided passes of a convolution (first: x -> ring, last: ring -> y) fetch their tiles with the TMA engine
+    // (fft_v32p.cuh: v32t_pass_kernel) instead of 32 register-direct loads per thread; 1: both, 2: first only, 3: last only
+    static const long v32t = env_long("FMB_V32T", 2);       // as measured (profiles/r2_experiments.txt, call 15): first pass only
+    CUtensorMap map_x, map_ring;
+    bool tma_a = false, tma_c = false;
+    if (v32t > 0 && two_ffts && kron_a == 0 && !pre_d && !post_d && v32p_tma_available() && rows_in > 0 && rows_in % 1024 == 0 &&
+        !(reinterpret_cast<uintptr_t>(x) & 15) && !(xcs & 1) && xcs >= rows_in && !(reinterpret_cast<uintptr_t>(ws) & 127)) {
+        // (a zero-padded input - Toeplitz - is better served by the pruned register-direct pass unless asked for with 1)
+        tma_a = (v32t == 1 || (v32t == 2 && rows_in == L)) && v32p_tensor_map(&map_x, x, rows_in, xcs, M) == FMB_OK;
+        tma_c = (v32t == 1 || v32t == 3) && v32p_tensor_map(&map_ring, ws, L, L, (int64_t)std::max(ns, 1) * slab) == FMB_OK;
+    }
     PipeScope pipe;
     if ((rc = pipe.begin(ns, st))) return rc;
+    // FMB_L2_PERSIST=1 (experiments): the ring of intermediates is the only data with reuse - ask the L2 to keep it
+    // (persisting access-policy window on the internal streams; everything else those kernels touch is streaming)
+    static const long l2_persist = env_long("FMB_L2_PERSIST", 0);
+    if (l2_persist > 0 && ns > 1) {
+        static bool limit_set = false;
+        if (!limit_set) {
+            int max_persist = 0, dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, dev);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist);
+            limit_set = true;
+        }
+        int max_window = 0, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, dev);
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        attr.accessPolicyWindow.base_ptr = ws;
+        attr.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)ns * (size_t)slab * (size_t)L * sizeof(C), (size_t)max_window);
+        attr.accessPolicyWindow.hitRatio = 1.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr.accessPolicyWindow.missProp = l2_persist == 2 ? cudaAccessPropertyNormal : cudaAccessPropertyStreaming;
+        for (int i = 0; i < ns; ++i) cudaStreamSetAttribute(pipe.stream(i), cudaStreamAttributeAccessPolicyWindow, &attr);
+    }
     void *const ws_base = ws;
     int64_t slab_idx = 0;
     for (int64_t c0 = 0; c0 < M; c0 += slab, ++slab_idx) {
         const int64_t nc = std::min(slab, M - c0);
+        int ring_col0 = 0;
         if (ns > 1) {
             st = pipe.stream(slab_idx);
             ws = (char *)ws_base + (size_t)(slab_idx % ns) * (size_t)slab * (size_t)L * sizeof(C);
+            ring_col0 = (int)((slab_idx % ns) * slab);
         }
         const unsigned tiles = (unsigned)(nc * 1024);          // lines; the launcher divides by its tile width
         FastArgs<C> base;
@@ -668,8 +709,10 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
             // zero padding to exactly twice the length (Toeplitz n = m = L/2): the padded half is never loaded and the first
             // radix-2 level of the butterflies is skipped (FMB_V32_PRUNE=0: masked loads, full butterflies)
             static const bool prune = env_long("FMB_V32_PRUNE", 1) != 0;
-            if (prune && two_ffts && !pre_d && rows_in * 2 == L) opt = V32_A_H;
-            if ((rc = launch_v32(opt, a, tiles, st))) return rc;
+            if (prune && two_ffts && !pre_d && rows_in * 2 == L && !tma_a) opt = V32_A_H;
+            if (tma_a) {                           // zero padding = rows outside the tensor map
+                if ((rc = launch_v32t(bwd && !two_ffts ? V32_A_FC : V32_A_F, a, map_x, (int)c0, tiles, st))) return rc;
+            } else if ((rc = launch_v32(opt, a, tiles, st))) return rc;
         }
         if (!two_ffts) {
             // ---- pass B: length R2 over n2 (contiguous in ws), lines k1; out y[k1 + R1 k2]
@@ -698,9 +741,11 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
                 a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[1].p;
                 unsigned opt = post_d ? (bwd ? V32_C_MPC : V32_C_MP) : (rows_out == L ? V32_C_N : V32_C_M);
                 static const bool prune = env_long("FMB_V32_PRUNE", 1) != 0;
-                if (prune && !post_d && rows_out * 2 == L) opt = V32_C_H;      // the dropped half of the rows is never computed
+                if (prune && !post_d && rows_out * 2 == L && !tma_c) opt = V32_C_H;      // the dropped half of the rows is never computed
                 if (tw_in_c) opt |= V32_C_TW;
-                if ((rc = launch_v32(opt, a, tiles, st))) return rc;
+                if (tma_c) {
+                    if ((rc = launch_v32t(opt, a, map_ring, ring_col0, tiles, st))) return rc;
+                } else if ((rc = launch_v32(opt, a, tiles, st))) return rc;
             }
         }
     }
@@ -764,6 +809,8 @@ static fmb_encode_tiled_fn encode_tiled_fn() {
     return fn;
 #endif
 }
+
+static bool v32p_tma_available() { return encode_tiled_fn() != nullptr; }
 
 // tensor of complex64 (as 8-byte words) [cols][rows / 1024][1024]; a request is a box of 8 words x 256 rows x 1 column
 static int v32p_tensor_map(CUtensorMap *map, const void *base, int64_t rows, int64_t col_stride, int64_t cols) {
@@ -938,7 +985,12 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
             set_error("workspace too small: need %lld bytes", (long long)workspace_bytes_cm(M, sizeof(C)));
             return FMB_ERR_WORKSPACE;
         }
-        if (v32_ok(sizeof(C)) && v32p_ok(direction, x, xcs, y, ycs)) return run_v32p(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
+        if (v32_ok(sizeof(C)) && v32p_ok(direction, x, xcs, y, ycs)) {
+            // the persistent kernel needs one CTA per SM co-resident (cooperative launch); where the context cannot give
+            // that, the per-pass kernels do the same work
+            rc = run_v32p(d, direction, x, xcs, y, ycs, M, ws, ws_bytes, st);
+            if (rc != FMB_ERR_FALLBACK) return rc;
+        }
         if (v32_ok(sizeof(C))) return run_v32(d, direction, x, xcs, y, ycs, M, ws, st);
         return run_fast<C>(d, direction, x, xcs, y, ycs, M, ws, st);
     }

@@ -177,10 +177,16 @@ __device__ __forceinline__ void v32p_tile(const FastArgs<float2> &a, float2 *con
     v32_pos<LOAD_T>(gt, jb, t);
     {
         const C *sl = LOAD_T ? smem + (jb << V32_LOGT) + t : smem + t * V32_RS + jb;
+        V32Chain h;
+        if (OPT & FO_IN_TWIDDLE) h = v32_chain_init(a, i0 + t, jb);
 #pragma unroll
         for (int m = 0; m < 32; ++m) {
             C val = LOAD_T ? sl[(32 * m) << V32_LOGT] : sl[32 * m];
             if (OPT & FO_IN_CONJ) val = cconj(val);
+            if (OPT & FO_IN_TWIDDLE) {
+                val = cmul(val, h.c[m & 3]);
+                if (m + 4 < 32) h.c[m & 3] = cmul(h.c[m & 3], h.s4);
+            }
             v[m] = val;
         }
     }
@@ -377,6 +383,47 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
     }
 }
 
+// ---- "V32T": ONE strided pass as an ordinary (non-persistent) launch whose tile is fetched by the TMA engine: thread 0
+// requests the four 16 KB boxes of the CTA's tile, everybody waits on the mbarrier and runs the same tile code as the
+// persistent kernel (landing buffer = exchange buffer).  Against the register-direct loads of v32_pass_kernel this takes
+// the 64-byte-segment loads (four L1 wavefronts per warp instruction) off the load/store pipe and leaves the registers
+// free while the tile is in flight; zero padding (Toeplitz) is the out-of-bounds fill of the tensor map.  Used by the
+// pipelined-slab schedule for the first and the last pass of a convolution (fft_engine.cu: run_v32, FMB_V32T).
+template <unsigned OPT>
+__global__ void __launch_bounds__(V32_NT, 2) v32t_pass_kernel(const __grid_constant__ FastArgs<float2> a, const __grid_constant__ CUtensorMap map,
+                                                             const int map_col0) {
+    typedef float2 C;
+    extern __shared__ unsigned char v32t_smem_raw[];
+    unsigned char *const base = v32t_smem_raw + ((128u - (v32p_smem_u32(v32t_smem_raw) & 127u)) & 127u);
+    const unsigned base_s = v32p_smem_u32(base), bar = base_s + (unsigned)V32P_BUF;
+    const int tid = threadIdx.x;
+    const unsigned line0 = blockIdx.x << V32_LOGT, col = line0 >> 10, i0 = line0 & 1023u;
+    if (tid == 0) {
+        v32p_mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        v32p_mbar_expect_tx(bar, V32P_TILE_BYTES);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            v32p_tma_box(base_s + q * 16384u, &map, bar, (int)i0, 256 * q, map_col0 + (int)col, 0x1000000000000000ull);
+    }
+    __syncthreads();                                   // the barrier is initialised before anybody polls it
+    v32p_mbar_wait(bar, 0u);
+    C *const out_col = a.out + (long long)col * a.out_cs;
+    v32p_tile<OPT>(a, reinterpret_cast<C *>(base), out_col, i0, tid, 0, []() {});
+}
+
+template <unsigned OPT> int launch_v32t_variant(const FastArgs<float2> &a, const CUtensorMap &map, int map_col0, unsigned lines, cudaStream_t st) {
+    constexpr size_t smem = V32P_BUF + 128 /* alignment slack */ + 64 /* mbarrier */;
+    static int attr_done = 0;
+    if (!attr_done) {
+        FMB_CUDA_OK(cudaFuncSetAttribute(v32t_pass_kernel<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = 1;
+    }
+    v32t_pass_kernel<OPT><<<lines >> V32_LOGT, V32_NT, smem, st>>>(a, map, map_col0);
+    FMB_LAUNCH_OK();
+    return FMB_OK;
+}
+
 // ---- variants (fft_engine.cu: run_v32p)
 enum V32PVariant { VP_F = 0, VP_FC = 1, VP_CV_N = 2, VP_CV_M = 3, VP_CVC_N = 4, VP_CVC_M = 5, VP_K = 6, VP_KC = 7 };
 constexpr unsigned V32P_K_A = FO_LOAD_T | FO_STORE_T, V32P_K_AC = V32P_K_A | FO_IN_CONJ;     // Kron(Fourier, Fourier): no twiddle,
@@ -395,8 +442,18 @@ int launch_v32p_variant(const V32PArgs &g, const CUtensorMap &mx, const CUtensor
     unsigned grid = (unsigned)grid_cap;
     if (grid > g.total_items) grid = g.total_items;
     if (grid == 0) return FMB_OK;
-    v32p_kernel<OA, OB, OC><<<grid, V32P_NT, V32P_SMEM, st>>>(g, mx, mr);
-    FMB_LAUNCH_OK();
+    // Cooperative launch: the runtime either makes ALL CTAs of the grid resident at once or refuses the launch.  The work
+    // list is only deadlock-free if they are (producers and consumers poll each other), so a context that cannot host one
+    // CTA per SM right now (MPS share, green context, SMs held by another stream) must get an error here, not a hang;
+    // the engine then falls back to the per-pass kernels (FMB_ERR_FALLBACK).
+    void *args[3] = {const_cast<V32PArgs *>(&g), const_cast<CUtensorMap *>(&mx), const_cast<CUtensorMap *>(&mr)};
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)v32p_kernel<OA, OB, OC>, dim3(grid), dim3(V32P_NT), args, V32P_SMEM, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) {
+        (void)cudaGetLastError();
+        return FMB_ERR_FALLBACK;
+    }
+    if (e != cudaSuccess) { set_error("persistent kernel launch failed: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+    g_launches.fetch_add(1);
     return FMB_OK;
 }
 

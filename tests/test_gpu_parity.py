@@ -756,3 +756,62 @@ def test_product_python_scalars_are_weakly_typed(fm):
     x = torch.from_numpy(rng.standard_normal((16, 2)).astype(np.float32)).cuda().to(torch.complex64)
     y1, y2 = (C / 3).forward(x), C.forward(x) / 3
     assert y1.dtype == torch.complex64 and float((y1 - y2).abs().max()) <= 1e-5 * float(y2.abs().max())
+
+
+@pytest.mark.gpu
+def test_toeplitz_norms_closed_form(fm):
+    """Toeplitz colNorms / rowNorms (fastmat/Toeplitz.pyx:371-625) from cumulative sums of |t|^2, single- and multi-level,
+    rectangular levels included, against the dense matrix by index placement; usable at 2^19 x 2^19 (O(n), no applies)."""
+    rng = np.random.default_rng(31)
+    for dr, dc in (((5, ), (3, )), ((3, ), (6, )), ((1, ), (5, )), ((3, 4), (2, 5)), ((2, 3, 2), (3, 2, 4))):
+        shape = tuple(a + b - 1 for a, b in zip(dr, dc))
+        t = (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)).astype(np.complex128)
+        T = fm.Toeplitz(t, split=list(dr))
+        D = T.reference().cpu().numpy()
+        assert D.shape == (int(np.prod(dr)), int(np.prod(dc)))
+        assert np.abs(T.colNorms.cpu().numpy() - np.linalg.norm(D, axis=0)).max() <= 1e-12 * np.linalg.norm(D)
+        assert np.abs(T.rowNorms.cpu().numpy() - np.linalg.norm(D, axis=1)).max() <= 1e-12 * np.linalg.norm(D)
+    n = 1 << 19
+    vc, vr = seeded(61, n).astype(np.complex64), seeded(62, n - 1).astype(np.complex64)
+    T = fm.Toeplitz(vc, vr)
+    launches = fm.launch_count()
+    cn = T.colNorms.cpu().numpy()
+    assert fm.launch_count() == launches                                   # closed form: not a single apply
+    a2, r2 = np.abs(vc.astype(np.complex128)) ** 2, np.abs(vr.astype(np.complex128)) ** 2
+    assert abs(cn[0] ** 2 - a2.sum()) <= 1e-9 * a2.sum()                    # column 0 is vecC
+    assert abs(cn[n - 1] ** 2 - (a2[0] + r2.sum())) <= 1e-9 * r2.sum()      # last column: t[0] and the whole row part
+    x = dev(seeded(63, n, 2).astype(np.complex64))
+    y = T.colNormalized.forward(x)                                          # usable at the BASELINE size now
+    ref = T.forward(x / torch.from_numpy(cn).cuda().reshape(-1, 1).to(torch.complex64))
+    assert float((y - ref).abs().max()) <= 1e-4 * float(ref.abs().max())
+
+
+@pytest.mark.gpu
+def test_largest_eigenvalue_and_scipy_linear_operator(fm):
+    """largestEigenValue (fastmat/Matrix.pyx:678-760) by power iteration on the device; scipyLinearOperator
+    (:977-1006) drives scipy's Krylov solvers with host vectors through apply_host."""
+    from scipy.sparse.linalg import svds
+    rng = np.random.default_rng(41)
+    ev = 0.8 * np.exp(2j * np.pi * rng.random(64)) * rng.random(64)         # eigenvalues of a circulant = fft of its first column
+    ev[3] = 5.0 * np.exp(0.7j)                                              # one dominant, well separated (complex) eigenvalue
+    C = fm.Circulant(np.fft.ifft(ev).astype(np.complex128))
+    assert abs(C.largestEigenValue - ev[3]) <= 1e-8 * abs(ev[3])
+    with pytest.raises(ValueError):
+        fm.Partial(fm.Fourier(8), rows=np.arange(4)).largestEigenValue
+    A = fm.Product(fm.Partial(fm.Fourier(64), rows=np.arange(0, 64, 3)), fm.Diag(rng.standard_normal(64) + 2.0))
+    op = A.scipyLinearOperator
+    assert op.shape == (22, 64)
+    x = rng.standard_normal(64) + 1j * rng.standard_normal(64)
+    assert np.abs(op.matvec(x) - A.forward(torch.from_numpy(x).cuda()).cpu().numpy()).max() <= 1e-10
+    s = svds(op, k=1, return_singular_vectors=False)[0]
+    assert abs(s - A.largestSingularValue) <= 1e-6 * s
+
+
+@pytest.mark.gpu
+def test_input_on_another_device_is_rejected(fm):
+    """A matrix belongs to the device that was current when it was built (plan constants live there)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    F = fm.Fourier(16)
+    with pytest.raises(RuntimeError):
+        F.forward(torch.zeros(16, dtype=torch.complex64, device='cuda:1'))

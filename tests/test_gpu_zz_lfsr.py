@@ -93,3 +93,35 @@ def test_partial_backward_scatter_holes_and_repeats(fm):        # noqa: F811
             for lay in ('F', 'C'):
                 assert np.array_equal(host(P.backward(dev(x, lay))), ref), (dt, lay)
             assert np.array_equal(host(P.backward(dev(x[:, 0]))), ref[:, 0])
+
+
+_SCATTER_FALLBACK = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import fastmat_b200 as fm
+rng = np.random.default_rng(5)
+n = 1000
+for idx in (np.array([7, 3, 7, 999, 0, 3, 7]), rng.integers(0, n, size=400), rng.permutation(n)[:333]):
+    P = fm.Partial(fm.Eye(n), rows=idx)
+    for dt in ('int8', 'float64', 'complex128'):
+        x = rng.integers(-100, 100, size=(idx.size, 5)).astype(dt)
+        ref = np.zeros((n, 5), dtype=dt)
+        ref[idx] = x
+        for _ in range(3):                                   # a race would not show every time
+            got = P.backward(torch.from_numpy(np.ascontiguousarray(x.T)).cuda().t()).cpu().numpy()
+            assert np.array_equal(got, ref), dt
+print('SCATTER_OK')
+'''
+
+
+def test_partial_backward_zero_scatter_path_is_deterministic_for_repeated_indices():
+    """Without the inverse table (FMB_PARTIAL_INVERSE=0, or a few rows out of a huge matrix) the backward is zero-fill +
+    scatter; repeated indices are reduced to their last occurrence at plan creation, so the result equals numpy's
+    y[idx] = x there as well instead of depending on which thread wrote last."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, FMB_PARTIAL_INVERSE='0')
+    r = subprocess.run([sys.executable, '-c', _SCATTER_FALLBACK], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and 'SCATTER_OK' in r.stdout, r.stdout + r.stderr

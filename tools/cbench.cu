@@ -8,6 +8,7 @@
 //     seconds > 0: additionally run back to back for at least that long and print the sustained figure
 // Prints one line: op, cols, ms per apply (best / mean of reps), algorithmic GB/s, fraction of FMB_PEAK_GBS (default
 // 6449.7), and two checksums of y (sum |y|^2 and an index-weighted sum) to compare variants with each other.
+#include <cuda_profiler_api.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
@@ -169,6 +170,13 @@ int main(int argc, char **argv) {
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
         sustained = ms / n;
+    }
+    if (getenv("CBENCH_PROFILE")) {                    // one apply inside a profiler range (ncu --replay-mode range: concurrent kernels as they run)
+        CK(cudaStreamSynchronize(st));
+        CK(cudaProfilerStart());
+        run();
+        CK(cudaStreamSynchronize(st));
+        CK(cudaProfilerStop());
     }
     double *cs;
     CK(cudaMalloc(&cs, 16)); CK(cudaMemset(cs, 0, 16));
