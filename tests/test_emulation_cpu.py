@@ -20,7 +20,10 @@ i64 = ctypes.c_int64
 
 @pytest.fixture(scope='module')
 def lib():
-    if not os.path.exists(EMUL):
+    src_dir = os.path.join(ROOT, 'fastmat_b200', 'csrc')
+    newest = max(os.path.getmtime(os.path.join(src_dir, f)) for f in os.listdir(src_dir))
+    newest = max(newest, os.path.getmtime(os.path.join(ROOT, 'include', 'fastmat_b200.h')))
+    if not os.path.exists(EMUL) or os.path.getmtime(EMUL) < newest:          # missing or older than the sources
         if shutil.which('nvcc') is None and not os.path.exists('/usr/local/cuda/bin/nvcc'):
             pytest.skip('no nvcc to build the emulation library')
         subprocess.check_call(['bash', os.path.join(ROOT, 'build.sh')], env=dict(os.environ, EMUL='1'), cwd=ROOT)
