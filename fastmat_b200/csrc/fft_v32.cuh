@@ -419,7 +419,11 @@ constexpr unsigned V32_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
 // 2 / 3 / 4 = 4 lines per CTA at 4 / 5 / 6 CTAs per SM (128 / 96 / 80 registers)
 template <unsigned OPT, int LOGT, int MINB> int launch_v32_inst(const FastArgs<float2> &a, unsigned lines, cudaStream_t st) {
     constexpr bool LOAD_T = (OPT & FO_LOAD_T) != 0, STORE_T = (OPT & FO_STORE_T) != 0;
-    constexpr size_t smem = (size_t)(1 << LOGT) * V32_RS * sizeof(float2);
+    // FMB_V32_SMEM_PAD (experiments): extra dynamic shared memory per CTA = a smaller L1 at unchanged occupancy.  These
+    // passes read their twiddle tables through L1; ~27 KB of L1 instead of ~93 KB costs +24 % - which is what three CTAs
+    // per SM (203 KB of shared memory) cost as well, whatever feeds them (profiles/r2_experiments.txt, calls 4, 19, 22, 23)
+    static const size_t smem_pad = getenv("FMB_V32_SMEM_PAD") ? (size_t)atol(getenv("FMB_V32_SMEM_PAD")) : 0;
+    const size_t smem = (size_t)(1 << LOGT) * V32_RS * sizeof(float2) + smem_pad;
     if (a.in_fs != (LOAD_T ? 1024 : 1) || a.in_is != (LOAD_T ? 1 : 1024) || a.out_ks != (STORE_T ? 1024 : 1) ||
         a.out_is != (STORE_T ? 1 : 1024) || a.I != 1024) {
         set_error("V32 pass: arguments do not describe the fixed 1024 x 1024 geometry");

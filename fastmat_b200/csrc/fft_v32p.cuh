@@ -389,8 +389,8 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
 // the 64-byte-segment loads (four L1 wavefronts per warp instruction) off the load/store pipe and leaves the registers
 // free while the tile is in flight; zero padding (Toeplitz) is the out-of-bounds fill of the tensor map.  Used by the
 // pipelined-slab schedule for the first and the last pass of a convolution (fft_engine.cu: run_v32, FMB_V32T).
-template <unsigned OPT>
-__global__ void __launch_bounds__(V32_NT, 2) v32t_pass_kernel(const __grid_constant__ FastArgs<float2> a, const __grid_constant__ CUtensorMap map,
+template <unsigned OPT, int MINB = 2>
+__global__ void __launch_bounds__(V32_NT, MINB) v32t_pass_kernel(const __grid_constant__ FastArgs<float2> a, const __grid_constant__ CUtensorMap map,
                                                              const int map_col0) {
     typedef float2 C;
     extern __shared__ unsigned char v32t_smem_raw[];
@@ -412,16 +412,23 @@ __global__ void __launch_bounds__(V32_NT, 2) v32t_pass_kernel(const __grid_const
     v32p_tile<OPT>(a, reinterpret_cast<C *>(base), out_col, i0, tid, 0, []() {});
 }
 
-template <unsigned OPT> int launch_v32t_variant(const FastArgs<float2> &a, const CUtensorMap &map, int map_col0, unsigned lines, cudaStream_t st) {
+template <unsigned OPT, int MINB> int launch_v32t_inst(const FastArgs<float2> &a, const CUtensorMap &map, int map_col0, unsigned lines, cudaStream_t st) {
     constexpr size_t smem = V32P_BUF + 128 /* alignment slack */ + 64 /* mbarrier */;
     static int attr_done = 0;
     if (!attr_done) {
-        FMB_CUDA_OK(cudaFuncSetAttribute(v32t_pass_kernel<OPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        FMB_CUDA_OK(cudaFuncSetAttribute(v32t_pass_kernel<OPT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = 1;
     }
-    v32t_pass_kernel<OPT><<<lines >> V32_LOGT, V32_NT, smem, st>>>(a, map, map_col0);
+    v32t_pass_kernel<OPT, MINB><<<lines >> V32_LOGT, V32_NT, smem, st>>>(a, map, map_col0);
     FMB_LAUNCH_OK();
     return FMB_OK;
+}
+template <unsigned OPT> int launch_v32t_variant(const FastArgs<float2> &a, const CUtensorMap &map, int map_col0, unsigned lines, cudaStream_t st) {
+#ifndef V32_LEAN
+    static const int occ3 = getenv("FMB_V32T_OCC") ? atoi(getenv("FMB_V32T_OCC")) : 0;       // experiments: 3 CTAs per SM (80 registers)
+    if (occ3) return launch_v32t_inst<OPT, 3>(a, map, map_col0, lines, st);
+#endif
+    return launch_v32t_inst<OPT, 2>(a, map, map_col0, lines, st);
 }
 
 // ---- variants (fft_engine.cu: run_v32p)
