@@ -220,7 +220,6 @@ struct HadamardPlan : PlanBase {
         o->kind = kind; o->num_rows = num_rows; o->num_cols = num_cols; o->inner_size = num_rows; o->passes_fwd = order > 12 ? 2 : 1;
         return FMB_OK;
     }
-    int64_t workspace_bytes(int, int64_t, int, int) const override { return 256; }   // grid-barrier counter of the fused kernel
     int apply(int, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dt_in, int dt_out,
               void *ws, int64_t ws_bytes, cudaStream_t st) const override {
         if (dt_in != dt_out) { set_error("Hadamard: output dtype must equal input dtype (promote(in, int8) = in)"); return FMB_ERR_TYPE; }

@@ -210,7 +210,8 @@ struct FwhtFastPass {
     int b, s;                  // this pass transforms index bits [s, s+b)
     int logT;                  // lines (consecutive low-bit values) per tile; 0 for the contiguous first pass
     int order;
-    long long tiles_per_col;
+    long long tiles_per_col;   // a power of two ...
+    int log_tpc;               // ... and its log2: tile -> (column, tile in column) by shift and mask, no 64-bit division
 };
 
 template <typename T, int LEV0> __device__ __forceinline__ void fwht16(T (&v)[16]) {
@@ -261,28 +262,30 @@ __device__ __forceinline__ void fwht_sub_chain(T (&v)[16], T *sl, T *gout_t, int
 }
 
 // One tile of one pass.  A tile is all 2^B "mid" values x Tn lines; a line is a low-bit value (strided passes) or, for the
-// contiguous first pass, one chunk of 2^B consecutive elements.  CG: read through L2 only (fused kernel: the input was
+// contiguous first pass, one chunk of 2^B consecutive elements.  CG: read through L2 only (the input was
 // written by other SMs earlier in the same launch).
-template <typename T, int B, bool CONTIG, bool CG>
+template <typename T, int B, bool CONTIG, bool CG, int LOGSTEP = -1>
 __device__ __forceinline__ void fwht_tile(const FwhtFastPass &p, long long tile, T *sm, int tid) {
     const int logT = p.logT, Tn = 1 << logT;
-    const long long col = tile / p.tiles_per_col;
-    const long long tin = tile - col * p.tiles_per_col;
+    const long long col = tile >> p.log_tpc;
+    const long long tin = tile & (p.tiles_per_col - 1);
     const int t = tid & (Tn - 1), q = tid >> logT;      // line-fastest thread order
     long long base;
     if (CONTIG) {
         base = ((tin << logT) + t) << B;                // chunk (tin*Tn + t) of the column
     } else {
         // tile -> (hi, lo0): Tn consecutive lo values starting at lo0, one hi value
-        const long long lo_tiles = ((long long)1 << p.s) >> logT;
-        const long long hi = tin / lo_tiles, lo0 = (tin - hi * lo_tiles) << logT;
+        const int log_lo = (LOGSTEP >= 0 ? LOGSTEP : p.s) - logT;                 // lo_tiles = 2^s / Tn
+        const long long hi = tin >> log_lo, lo0 = (tin & (((long long)1 << log_lo) - 1)) << logT;
         base = (hi << (p.s + B)) + lo0 + t;
     }
     const T *gin = (const T *)p.in + col * p.in_cs + base;
     T *gout = (T *)p.out + col * p.out_cs + base;
     constexpr int RSL = (1 << B) + ((1 << B) >> 4) + 1; // padded line stride in shared memory (odd -> conflict free)
     T *sl = sm + t * RSL;
-    const long long step = CONTIG ? 1ll : ((long long)1 << p.s);
+    // LOGSTEP >= 0: the stride of the strided pass is a compile-time constant (order 20: 2^12 elements), so the sixteen
+    // loads and stores of a thread are one base register plus immediates instead of a 64-bit multiply-add each
+    const long long step = CONTIG ? 1ll : (LOGSTEP >= 0 ? ((long long)1 << (LOGSTEP >= 0 ? LOGSTEP : 0)) : ((long long)1 << p.s));
     T v[16];
     // ---- first sub-stage: bits [0, 4) of mid straight from global memory
     const T *src = gin + (long long)(q << 4) * step;
@@ -312,72 +315,22 @@ __device__ __forceinline__ void fwht_tile(const FwhtFastPass &p, long long tile,
     }
 }
 
-template <typename T, int B, bool CONTIG> __global__ void __launch_bounds__(512) fwht_fast_kernel(const __grid_constant__ FwhtFastPass p) {
+template <typename T, int B, bool CONTIG, int LOGSTEP = -1> __global__ void __launch_bounds__(512) fwht_fast_kernel(const __grid_constant__ FwhtFastPass p) {
     extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
-    fwht_tile<T, B, CONTIG, false>(p, (long long)blockIdx.x, reinterpret_cast<T *>(fwht_smem_raw), (int)threadIdx.x);
-}
-
-// ---- both passes of a two-pass transform in ONE persistent launch.  Columns flow through in slabs small enough for the
-// slab to stay in L2 between its first and its second pass: phase k runs pass 1 of slab k and pass 2 of slab k-1 (static
-// tile lists over all co-resident CTAs), phases are separated by a grid-wide barrier (release-increment + relaxed poll of
-// a global counter; pass 2 reads through L2 only, so no L1 invalidation is needed).  HBM then sees every element once
-// in and once out instead of twice.
-struct FwhtFused2 {
-    FwhtFastPass p1, p2;          // in / out for column 0 of slab 0 (p2.in == p2.out == y)
-    long long M;                  // columns
-    int slab_cols, nslabs;
-    unsigned *barrier;
-};
-
-__device__ __forceinline__ void fwht_red_release(unsigned *p, unsigned v) {
-    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned fwht_ld_relaxed(const unsigned *p) {
-    unsigned v;
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
-template <typename T, int B0, int B1> __global__ void __launch_bounds__(512) fwht_fused2_kernel(const __grid_constant__ FwhtFused2 f) {
-    extern __shared__ __align__(16) unsigned char fwht_smem_raw[];
-    T *sm = reinterpret_cast<T *>(fwht_smem_raw);
-    const int tid = threadIdx.x;
-    for (int ph = 0; ph <= f.nslabs; ++ph) {
-        const long long c1 = (long long)ph * f.slab_cols, c2 = (long long)(ph - 1) * f.slab_cols;
-        const long long n1 = (ph < f.nslabs) ? (f.M - c1 < f.slab_cols ? f.M - c1 : f.slab_cols) * f.p1.tiles_per_col : 0;
-        const long long n2 = (ph >= 1) ? (f.M - c2 < f.slab_cols ? f.M - c2 : f.slab_cols) * f.p2.tiles_per_col : 0;
-        for (long long idx = blockIdx.x; idx < n1 + n2; idx += gridDim.x) {
-            if (idx < n1) fwht_tile<T, B0, true, false>(f.p1, c1 * f.p1.tiles_per_col + idx, sm, tid);
-            else fwht_tile<T, B1, false, true>(f.p2, c2 * f.p2.tiles_per_col + (idx - n1), sm, tid);
-            __syncthreads();                            // shared memory is reused by the next tile
-        }
-        // ---- grid barrier
-        __syncthreads();
-        if (tid == 0) {
-            fwht_red_release(f.barrier, 1u);
-            const unsigned target = (unsigned)(ph + 1) * gridDim.x;
-            while (fwht_ld_relaxed(f.barrier) < target) __nanosleep(20);
-        }
-        __syncthreads();
-    }
-}
-
-template <typename T, int B0, int B1>
-static int fwht_fused2_launch(const FwhtFused2 &f, size_t smem, cudaStream_t st) {
-    static int grid_cap = 0;
-    if (!grid_cap) {
-        FMB_CUDA_OK(cudaFuncSetAttribute(fwht_fused2_kernel<T, B0, B1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        int per_sm = 0;
-        FMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fwht_fused2_kernel<T, B0, B1>, 512, smem));
-        if (per_sm < 1) { set_error("fused FWHT kernel does not fit on an SM"); return FMB_ERR_CUDA; }
-        grid_cap = per_sm * device_props().sm_count;     // all CTAs must be resident: they meet at a grid barrier
-    }
-    fwht_fused2_kernel<T, B0, B1><<<grid_cap, 512, smem, st>>>(f);
-    FMB_LAUNCH_OK();
-    return FMB_OK;
+    fwht_tile<T, B, CONTIG, false, LOGSTEP>(p, (long long)blockIdx.x, reinterpret_cast<T *>(fwht_smem_raw), (int)threadIdx.x);
 }
 
 template <typename T> static int fwht_fast_launch(const FwhtFastPass &p, unsigned grid, int threads, size_t smem, cudaStream_t st) {
+    if (p.b == 8 && p.s == 12) {                        // second pass of order 20 (the BASELINE shape): compile-time stride
+        static int attr_done = 0;
+        if (!attr_done) {
+            FMB_CUDA_OK(cudaFuncSetAttribute(fwht_fast_kernel<T, 8, false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 << 10));
+            attr_done = 1;
+        }
+        fwht_fast_kernel<T, 8, false, 12><<<grid, threads, smem, st>>>(p);
+        FMB_LAUNCH_OK();
+        return FMB_OK;
+    }
 #define FMB_FWHT_CASE(BB)                                                                                              \
     case BB: {                                                                                                         \
         static int attr_done = 0;                                                                                      \
@@ -400,46 +353,8 @@ template <typename T> static int fwht_fast_launch(const FwhtFastPass &p, unsigne
     return FMB_OK;
 }
 
-template <typename T, int B1>
-static int fwht_fused2(int order, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) {
-    static const long slab_mb = getenv("FMB_FWHT_FUSED_SLAB_MB") ? atol(getenv("FMB_FWHT_FUSED_SLAB_MB")) : 32;
-    FwhtFused2 f;
-    memset(&f, 0, sizeof(f));
-    f.M = M;
-    int64_t slab = (int64_t)(((size_t)slab_mb << 20) / (((size_t)1 << order) * sizeof(T)));
-    if (slab < 1) slab = 1;
-    f.slab_cols = (int)std::min<int64_t>(slab, M);
-    f.nslabs = (int)((M + f.slab_cols - 1) / f.slab_cols);
-    f.barrier = (unsigned *)ws;
-    FMB_CUDA_OK(cudaMemsetAsync(ws, 0, 256, st));
-    f.p1.in = x; f.p1.in_cs = xcs; f.p1.out = y; f.p1.out_cs = ycs;
-    f.p1.b = 12; f.p1.s = 0; f.p1.order = order; f.p1.logT = 1;                 // two 4096-element chunks per tile: 512 threads
-    f.p1.tiles_per_col = ((long long)1 << (order - 12)) >> 1;
-    int logT2 = 0;
-    while ((16 * 512 >> B1) > (1 << logT2)) ++logT2;                            // 512 threads x 16 values / 2^B1 mid values
-    f.p2.in = y; f.p2.in_cs = ycs; f.p2.out = y; f.p2.out_cs = ycs;
-    f.p2.b = B1; f.p2.s = 12; f.p2.order = order; f.p2.logT = logT2;
-    f.p2.tiles_per_col = ((long long)1 << (order - B1)) >> logT2;
-    const size_t e1 = (size_t)2 * ((1 << 12) + (1 << 8) + 1), e2 = ((size_t)1 << logT2) * ((size_t)(1 << B1) + ((size_t)(1 << B1) >> 4) + 1);
-    const size_t smem = std::max(e1, e2) * sizeof(T);
-    return fwht_fused2_launch<T, 12, B1>(f, smem, st);
-}
-
 template <typename T>
 static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes, cudaStream_t st) {
-    // orders 16..20 (12 + 4..8 bits): both passes fused in one persistent launch with the slab resident in L2.  Opt-in:
-    // measured on B200 in round 1 it is correct but slower than two launches over a 512 MiB slab (3.9 ms vs 2.9 ms per
-    // 1024 float32 columns at order 20): ~130 grid barriers cost more than the halved HBM traffic saves.
-    static const long fused_on = getenv("FMB_FWHT_FUSED") ? atol(getenv("FMB_FWHT_FUSED")) : 0;
-    if (fused_on && order >= 16 && order <= 20 && ws != nullptr && ws_bytes >= 256 && M >= 1) {
-        switch (order - 12) {
-            case 4: return fwht_fused2<T, 4>(order, x, xcs, y, ycs, M, ws, st);
-            case 5: return fwht_fused2<T, 5>(order, x, xcs, y, ycs, M, ws, st);
-            case 6: return fwht_fused2<T, 6>(order, x, xcs, y, ycs, M, ws, st);
-            case 7: return fwht_fused2<T, 7>(order, x, xcs, y, ycs, M, ws, st);
-            default: return fwht_fused2<T, 8>(order, x, xcs, y, ycs, M, ws, st);
-        }
-    }
     // bit ranges per pass: a contiguous first pass of up to 12 bits, then strided passes of 4..8 bits
     std::vector<int> bits;
     if (order <= 12) bits.push_back(order);
@@ -502,6 +417,7 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
             p.logT = logT;
             const int threads = (1 << (p.b - 4)) << logT;
             p.tiles_per_col = ((long long)1 << (order - p.b)) >> logT;
+            p.log_tpc = order - p.b - logT;
             const long long grid = p.tiles_per_col * nc;
             if (grid > 2147483647LL || threads > 512 || threads < 1) { set_error("FWHT fast path: bad geometry"); return FMB_ERR_VALUE; }
             const size_t smem = (size_t)(1 << logT) * ((size_t)(1 << p.b) + ((size_t)(1 << p.b) >> 4) + 1) * sizeof(T);

@@ -522,43 +522,49 @@ def _run_with_env(env, code):
     return r.stdout
 
 
-_FUSED_CHECK = r'''
+_SWITCH_CHECK = r'''
 import sys, numpy as np, torch
 sys.path.insert(0, '.')
 import fastmat_b200 as fm
 from oracle import fastmat_oracle as orc
 rng = np.random.default_rng(5)
 def crand(*s): return (rng.standard_normal(s) + 1j * rng.standard_normal(s))
-def dev(a): return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
-n = 2 ** 16
-x = crand(n, 5)
-for dt, tol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
-    xd = dev(x.astype(dt))
-    nx = np.linalg.norm(x, axis=0).max() * np.log2(n)
-    F = fm.Fourier(n)
-    assert np.abs(F.forward(xd).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
-    assert np.abs(F.backward(xd).cpu().numpy() - orc.fourier_backward(x)).max() / nx < tol
-c = crand(n)
-C = fm.Circulant(c.astype(np.complex64))
-xd = dev(x.astype(np.complex64))
-nc = np.linalg.norm(c) * np.linalg.norm(x, axis=0).max() * np.log2(n)
-assert np.abs(C.forward(xd).cpu().numpy() - orc.circulant_forward(c, x)).max() / nc < 1e-5
-assert np.abs(C.backward(xd).cpu().numpy() - orc.circulant_backward(c, x)).max() / nc < 1e-5
-T = fm.Toeplitz(c[:40000].astype(np.complex64), c[:20000].astype(np.complex64))
-xt = dev(x[:20001].astype(np.complex64))
-assert np.abs(T.forward(xt).cpu().numpy() - orc.toeplitz_forward(c[:40000], c[:20000], x[:20001])).max() / nc < 1e-5
-xi = rng.integers(-2 ** 31, 2 ** 31 - 1, size=(2 ** 17, 7)).astype(np.int32)
-assert np.array_equal(fm.Hadamard(17).forward(dev(xi)).cpu().numpy(), orc.hadamard_forward(xi))
-xf = rng.standard_normal((2 ** 16, 3)).astype(np.float32)
-assert np.array_equal(fm.Hadamard(16).forward(dev(xf)).cpu().numpy(), orc.hadamard_forward(xf))
-print('fused ok', fm.launch_count())
+def dev(a, rm=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if rm else t.t().contiguous().t()
+n, m = 2 ** 20, 13                                     # enough columns for the pipelined-slab schedule, ragged last slab
+x = crand(n, m).astype(np.complex64)
+c = crand(n).astype(np.complex64)
+C = fm.Circulant(c)
+nc = np.linalg.norm(c) * np.linalg.norm(x, axis=0).max() * 20
+chk = [0, 7, 12]
+for rm in (False, True):
+    yf, yb = C.forward(dev(x, rm)).cpu().numpy(), C.backward(dev(x, rm)).cpu().numpy()
+    assert np.abs(yf[:, chk] - orc.circulant_forward(c, x[:, chk])).max() / nc < 1e-5
+    assert np.abs(yb[:, chk] - orc.circulant_backward(c, x[:, chk])).max() / nc < 1e-5
+nt = n // 2
+vc, vr = c[:nt].copy(), c[nt:2 * nt - 1].copy()
+T = fm.Toeplitz(vc, vr)
+xt = x[:nt]
+yf, yb = T.forward(dev(xt)).cpu().numpy(), T.backward(dev(xt)).cpu().numpy()
+assert np.abs(yf[:, chk] - orc.toeplitz_forward(vc, vr, xt[:, chk])).max() / nc < 1e-5
+assert np.abs(yb[:, chk] - orc.toeplitz_backward(vc, vr, xt[:, chk])).max() / nc < 1e-5
+F = fm.Fourier(n)
+nx = np.linalg.norm(x, axis=0).max() * 20
+assert np.abs(F.forward(dev(x)).cpu().numpy()[:, chk] - orc.fourier_forward(x[:, chk])).max() / nx < 1e-5
+print('switches ok', fm.launch_count())
 '''
 
 
-def test_fused_persistent_kernels_opt_in(fm):
-    """The opt-in single-launch pipelines (FMB_FUSED=1: FFT / convolution, FMB_FWHT_FUSED=1: Hadamard) stay correct."""
-    out = _run_with_env({'FMB_FUSED': '1', 'FMB_FWHT_FUSED': '1'}, _FUSED_CHECK)
-    assert 'fused ok' in out
+@pytest.mark.parametrize('env', [{'FMB_V32T': '1'}, {'FMB_V32T': '0', 'FMB_V32_PRUNE': '0'}, {'FMB_V32_TWM': '1', 'FMB_V32P': '2'},
+                                 {'FMB_V32_OCC': '1', 'FMB_V32_MSHAPE': '3', 'FMB_V32P': '0'}, {'FMB_RM_CHUNK': '0', 'FMB_NO_V32': '1'}],
+                         ids=lambda e: ','.join('%s=%s' % kv for kv in e.items()))
+def test_runtime_switches_keep_results_within_tolerance(fm, env):
+    """The A/B switches of the 2^20 kernels (DESIGN.md section 6: TMA-fed passes, pruning, twiddle placement, tile shapes,
+    persistent kernel for convolutions, generic row-major route, 16-value fast path) all compute the same operator:
+    Circulant / Toeplitz / Fourier at the BASELINE sizes against the oracle, both layouts."""
+    out = _run_with_env(env, _SWITCH_CHECK)
+    assert 'switches ok' in out
 
 
 # ------------------------------------------------------------------------------------------- pipelined-slab schedule

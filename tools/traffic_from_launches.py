@@ -37,7 +37,7 @@ for r in rows:
         elif d['Metric Name'] == 'dram__bytes_write.sum':
             k['wr'] += v * scale
 # only the transform kernels of the library (the bench also launches torch's RNG / copy kernels)
-ours = {k: v for k, v in per.items() if 'fmb::' in k or 'v32_pass' in k or 'fast_pass' in k or 'fwht' in k}
+ours = {k: v for k, v in per.items() if 'fmb::' in k or 'v32_pass' in k or 'v32t_pass' in k or 'v32p_kernel' in k or 'fast_pass' in k or 'fwht' in k}
 tot_ns = sum(v['ns'] for v in ours.values())
 N, COLS = 1 << 20, 1024
 out = {'source': src + ' (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none; '
