@@ -510,6 +510,13 @@ def run_ours(args):
         except Exception as e:
             extras['lfsr_circulant_forward_o20_f32'] = {'error': repr(e)}
         del xf
+        # sizes fastmat's planner actually emits that still run the generic run-time-radix kernels (SURVEY appendix B:
+        # 2^a 3^b paddings such as 6144 and 110592; pass lengths below 256): measured, not yet specialised
+        for nn, mm in ((1 << 14, 1024), (6144, 1024), (110592, 256)):
+            Fs = fm.Fourier(nn)
+            xs_ = crandn(nn, mm)
+            rec('fourier_forward_%d_c64_generic_kernels' % nn, lambda: Fs.forward(xs_), mm, 16.0 * nn, k=10, sustain=0)
+            del xs_, Fs
         x16 = crandn(1 << 16, 64).to(torch.complex128)
         F16 = fm.Fourier(1 << 16)
         rec('fourier_forward_2^16_c128_64cols', lambda: F16.forward(x16), 64, 32.0 * (1 << 16), k=20)

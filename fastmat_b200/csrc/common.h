@@ -120,7 +120,6 @@ const DeviceProps &device_props();
 // k on stream(k), and joins them back, so that consecutive slabs overlap and the caller still sees stream order.
 constexpr int FMB_MAX_PIPE = 6;
 struct PipeScope {
-    std::unique_lock<std::mutex> lock;
     int ns = 1;
     cudaStream_t caller = nullptr;
     void *pool_ = nullptr;              // the device's stream pool (fft_engine.cu)

@@ -295,15 +295,14 @@ int64_t ConvEngine::workspace_bytes_cm(int64_t M, size_t csize) const {
     return generic;
 }
 
-// internal streams of the pipelined-slab schedule (common.h: PipeScope): one set per device, shared by all plans; `mu`
-// serialises the (host-side, asynchronous) issue of one apply so that fork / join events of concurrent callers cannot
-// interleave
+// internal streams of the pipelined-slab schedule (common.h: PipeScope): one set per HOST THREAD and device, shared by all
+// plans that thread applies.  Concurrent callers (different host threads, distinct workspaces) therefore issue their
+// applies independently - round 1 had one set per device behind a mutex that serialised the host-side issue.
 struct StreamPool {
-    std::mutex mu;
     cudaStream_t s[FMB_MAX_PIPE] = {};
     cudaEvent_t fork = nullptr, join[FMB_MAX_PIPE] = {};
     bool ready = false;
-    int ensure() {                       // called with mu held, on the pool of the current device
+    int ensure() {                       // on the calling thread's pool of the current device
         if (ready) return FMB_OK;
         for (int i = 0; i < FMB_MAX_PIPE; ++i) {
             FMB_CUDA_OK(cudaStreamCreateWithFlags(&s[i], cudaStreamNonBlocking));
@@ -313,9 +312,15 @@ struct StreamPool {
         ready = true;
         return FMB_OK;
     }
+    ~StreamPool() {                      // thread exit; errors (context already gone) are of no consequence
+        if (!ready) return;
+        for (int i = 0; i < FMB_MAX_PIPE; ++i) { cudaStreamDestroy(s[i]); cudaEventDestroy(join[i]); }
+        cudaEventDestroy(fork);
+        (void)cudaGetLastError();
+    }
 };
 constexpr int FMB_MAX_DEVICES = 64;
-static StreamPool g_pools[FMB_MAX_DEVICES];     // one per device ordinal (streams belong to a device)
+static thread_local StreamPool g_pools[FMB_MAX_DEVICES];     // one per device ordinal (streams belong to a device)
 
 int PipeScope::begin(int ns_, cudaStream_t st) {
     caller = st;
@@ -326,7 +331,6 @@ int PipeScope::begin(int ns_, cudaStream_t st) {
     if (dev < 0 || dev >= FMB_MAX_DEVICES) { ns = 1; return FMB_OK; }
     StreamPool &pool = g_pools[dev];
     pool_ = &pool;
-    lock = std::unique_lock<std::mutex>(pool.mu);
     int rc = pool.ensure();
     if (rc) return rc;
     FMB_CUDA_OK(cudaEventRecord(pool.fork, st));
@@ -343,7 +347,6 @@ int PipeScope::end() {
         FMB_CUDA_OK(cudaEventRecord(pool.join[i], pool.s[i]));
         FMB_CUDA_OK(cudaStreamWaitEvent(caller, pool.join[i], 0));
     }
-    lock.unlock();
     return FMB_OK;
 }
 
@@ -627,11 +630,12 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
     static const long v32t = env_long("FMB_V32T", 2);       // as measured (profiles/r2_experiments.txt, call 15): first pass only
     CUtensorMap map_x, map_ring;
     bool tma_a = false, tma_c = false;
-    if (v32t > 0 && two_ffts && kron_a == 0 && !pre_d && !post_d && v32p_tma_available() && rows_in > 0 && rows_in % 1024 == 0 &&
+    static const long v32t_plain = env_long("FMB_V32T_PLAIN", 0);       // experiments: also the first pass of a plain transform
+    if (v32t > 0 && (two_ffts || v32t_plain) && kron_a == 0 && !pre_d && !post_d && v32p_tma_available() && rows_in > 0 && rows_in % 1024 == 0 &&
         !(reinterpret_cast<uintptr_t>(x) & 15) && !(xcs & 1) && xcs >= rows_in && !(reinterpret_cast<uintptr_t>(ws) & 127)) {
         // (a zero-padded input - Toeplitz - is better served by the pruned register-direct pass unless asked for with 1)
         tma_a = (v32t == 1 || (v32t == 2 && rows_in == L)) && v32p_tensor_map(&map_x, x, rows_in, xcs, M) == FMB_OK;
-        tma_c = (v32t == 1 || v32t == 3) && v32p_tensor_map(&map_ring, ws, L, L, (int64_t)std::max(ns, 1) * slab) == FMB_OK;
+        tma_c = two_ffts && (v32t == 1 || v32t == 3) && v32p_tensor_map(&map_ring, ws, L, L, (int64_t)std::max(ns, 1) * slab) == FMB_OK;
     }
     PipeScope pipe;
     if ((rc = pipe.begin(ns, st))) return rc;
@@ -711,7 +715,7 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
             static const bool prune = env_long("FMB_V32_PRUNE", 1) != 0;
             if (prune && two_ffts && !pre_d && rows_in * 2 == L && !tma_a) opt = V32_A_H;
             if (tma_a) {                           // zero padding = rows outside the tensor map
-                if ((rc = launch_v32t(bwd && !two_ffts ? V32_A_FC : V32_A_F, a, map_x, (int)c0, tiles, st))) return rc;
+                if ((rc = launch_v32t((bwd && !two_ffts) ? V32_A_FC : V32_A_F, a, map_x, (int)c0, tiles, st))) return rc;
             } else if ((rc = launch_v32(opt, a, tiles, st))) return rc;
         }
         if (!two_ffts) {

@@ -821,3 +821,40 @@ def test_input_on_another_device_is_rejected(fm):
     F = fm.Fourier(16)
     with pytest.raises(RuntimeError):
         F.forward(torch.zeros(16, dtype=torch.complex64, device='cuda:1'))
+
+
+@pytest.mark.gpu
+def test_concurrent_host_threads_on_one_plan(fm):
+    """include/fastmat_b200.h: apply is safe to call concurrently on one plan from several host threads / streams with
+    distinct workspaces.  Each host thread has its own internal streams for the pipelined-slab schedule (no issue mutex);
+    four threads x three applies of one Circulant 2^20 plan on their own streams give the serial results bit for bit."""
+    import threading
+    n, m = 2 ** 20, 13
+    rng = np.random.default_rng(123)
+    C = fm.Circulant((rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64))
+    g = torch.Generator(device='cuda').manual_seed(5)
+    xs = [torch.complex(torch.randn((m, n), device='cuda', generator=g), torch.randn((m, n), device='cuda', generator=g)).t()
+          for _ in range(4)]
+    ref = [C.forward(x) for x in xs]
+    torch.cuda.synchronize()
+    out, errs = [None] * 4, []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(3):
+                    y = C.forward(xs[i])
+            s.synchronize()
+            out[i] = y
+        except Exception as e:                                   # noqa: BLE001
+            errs.append(repr(e))
+
+    threads = [threading.Thread(target=work, args=(i, )) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errs, errs
+    for i in range(4):
+        assert torch.equal(out[i], ref[i]), i
