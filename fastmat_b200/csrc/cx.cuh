@@ -42,6 +42,58 @@ template <typename C> FMB_HD C cmul_mi(C a) { return mk<C>(a.y, -a.x); }   // a 
 template <typename C> FMB_HD C cmul_pi(C a) { return mk<C>(-a.y, a.x); }   // a * (+i)
 template <typename C> FMB_HD C cscale(C a, typename real_of<C>::type s) { return mk<C>(a.x * s, a.y * s); }
 
+// ---- fused butterflies.  The FFT kernels are bound by FP32 issue, so a twiddle multiplication that
+// feeds a radix-2 butterfly is not done as "multiply, then add and subtract" (4 + 4 operations per complex pair) but
+// folded into fused multiply-adds:  t0 = a + w z  is two FMAs per component, and  t1 = a - w z = 2 a - t0  one more:
+// 6 operations.  Two twiddled inputs  t2 = w1 b + w3 d,  dd = w1 b - w3 d = 2 (w1 b) - t2  cost 10 instead of 12.
+FMB_HD float fmb_fma(float a, float b, float c) { return fmaf(a, b, c); }
+FMB_HD double fmb_fma(double a, double b, double c) { return fma(a, b, c); }
+template <typename C> FMB_HD void bfly_w(C a, C z, typename real_of<C>::type wr, typename real_of<C>::type wi, C &t0, C &t1) {
+    typedef typename real_of<C>::type S;
+    t0.x = fmb_fma(wr, z.x, fmb_fma(-wi, z.y, a.x));
+    t0.y = fmb_fma(wr, z.y, fmb_fma(wi, z.x, a.y));
+    t1.x = fmb_fma((S)2, a.x, -t0.x);
+    t1.y = fmb_fma((S)2, a.y, -t0.y);
+}
+// t0 = a + w z only (the other half of the butterfly is not needed)
+template <typename C> FMB_HD C add_w(C a, C z, typename real_of<C>::type wr, typename real_of<C>::type wi) {
+    return mk<C>(fmb_fma(wr, z.x, fmb_fma(-wi, z.y, a.x)), fmb_fma(wr, z.y, fmb_fma(wi, z.x, a.y)));
+}
+template <typename C>
+FMB_HD void bfly_ww(C b, C d, typename real_of<C>::type w1r, typename real_of<C>::type w1i, typename real_of<C>::type w3r,
+                    typename real_of<C>::type w3i, C &t2, C &dd) {
+    typedef typename real_of<C>::type S;
+    const C p = mk<C>(fmb_fma(w1r, b.x, -w1i * b.y), fmb_fma(w1r, b.y, w1i * b.x));
+    t2.x = fmb_fma(w3r, d.x, fmb_fma(-w3i, d.y, p.x));
+    t2.y = fmb_fma(w3r, d.y, fmb_fma(w3i, d.x, p.y));
+    dd.x = fmb_fma((S)2, p.x, -t2.x);
+    dd.y = fmb_fma((S)2, p.y, -t2.y);
+}
+// radix-4 butterfly whose inputs 1, 2, 3 still carry the twiddles w1, w2, w3 (input 0 none):
+//   X[k] = v0 + (-i)^k w1 v1 + (-1)^k w2 v2 + (i)^k w3 v3      -> v0, v1, v2, v3 = X[0], X[1], X[2], X[3]
+template <typename C>
+FMB_HD void dft4_tw(C &v0, C &v1, C &v2, C &v3, typename real_of<C>::type w1r, typename real_of<C>::type w1i,
+                    typename real_of<C>::type w2r, typename real_of<C>::type w2i, typename real_of<C>::type w3r,
+                    typename real_of<C>::type w3i) {
+    C t0, t1, t2, d;
+    bfly_w(v0, v2, w2r, w2i, t0, t1);
+    bfly_ww(v1, v3, w1r, w1i, w3r, w3i, t2, d);
+    v0 = cadd(t0, t2); v2 = csub(t0, t2);
+    v1 = mk<C>(t1.x + d.y, t1.y - d.x);
+    v3 = mk<C>(t1.x - d.y, t1.y + d.x);
+}
+// ... the same with w2 = -i (no multiplication for input 2)
+template <typename C>
+FMB_HD void dft4_tw_mi(C &v0, C &v1, C &v2, C &v3, typename real_of<C>::type w1r, typename real_of<C>::type w1i,
+                       typename real_of<C>::type w3r, typename real_of<C>::type w3i) {
+    const C t0 = mk<C>(v0.x + v2.y, v0.y - v2.x), t1 = mk<C>(v0.x - v2.y, v0.y + v2.x);
+    C t2, d;
+    bfly_ww(v1, v3, w1r, w1i, w3r, w3i, t2, d);
+    v0 = cadd(t0, t2); v2 = csub(t0, t2);
+    v1 = mk<C>(t1.x + d.y, t1.y - d.x);
+    v3 = mk<C>(t1.x - d.y, t1.y + d.x);
+}
+
 // ---- forward DFTs (kernel e^{-2 pi i rk/P}), in place.  The result X[q] ends up at array position
 // ---- outpos<P>(q) (digit-reversed for the composite radices) so that no register shuffling is needed.
 template <int P> FMB_HD constexpr int outpos(int q) { return q; }
@@ -82,6 +134,8 @@ template <typename C> FMB_HD void dft8(C *v) {
 }
 
 // radix 16: r = 4*r1 + r0, q = k0 + 4*k1; X[k0 + 4 k1] = sum_{r0} W16^{r0 k0} W4^{r0 k1} [sum_{r1} v[4 r1 + r0] W4^{r1 k0}]
+// The twiddles W16^{r0 k0} between the two levels are folded into the second level's butterflies (dft4_tw): 154 instead of
+// 164 operations.  -DFMB_PLAIN_BUTTERFLIES restores the multiply-then-butterfly form of round 1.
 template <typename C> FMB_HD void dft16(C *v) {
     typedef typename real_of<C>::type S;
     const S h = (S)0.70710678118654752440084436210485;
@@ -89,6 +143,12 @@ template <typename C> FMB_HD void dft16(C *v) {
     const S s1 = (S)0.38268343236508977172845998403040;   // sin(pi/8)
 #pragma unroll
     for (int r0 = 0; r0 < 4; ++r0) dft4(v[r0], v[4 + r0], v[8 + r0], v[12 + r0]);   // y[r0][k0] at v[4*k0 + r0]
+#ifndef FMB_PLAIN_BUTTERFLIES
+    dft4(v[0], v[1], v[2], v[3]);
+    dft4_tw(v[4], v[5], v[6], v[7], c1, -s1, h, -h, s1, -c1);                       // k0 = 1: W16^1, W16^2, W16^3
+    dft4_tw_mi(v[8], v[9], v[10], v[11], h, -h, -h, -h);                            // k0 = 2: W16^2, W16^4 = -i, W16^6
+    dft4_tw(v[12], v[13], v[14], v[15], s1, -c1, -h, -h, -c1, s1);                  // k0 = 3: W16^3, W16^6, W16^9
+#else
     // twiddles W16^{r0*k0} on v[4*k0 + r0]
     C a;
     // k0 = 1: W^1, W^2, W^3
@@ -105,6 +165,7 @@ template <typename C> FMB_HD void dft16(C *v) {
     a = v[15]; v[15] = mk<C>(-a.x * c1 - a.y * s1, a.x * s1 - a.y * c1);              // W16^9 = -c1 + i s1
 #pragma unroll
     for (int k0 = 0; k0 < 4; ++k0) dft4(v[4 * k0], v[4 * k0 + 1], v[4 * k0 + 2], v[4 * k0 + 3]);
+#endif
 }
 
 // generic odd prime radix, constants taken from the unit-root table of the transform (wp[r] = e^{-2 pi i r/P})

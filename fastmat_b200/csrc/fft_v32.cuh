@@ -55,12 +55,42 @@ template <int K, typename C> __device__ __forceinline__ C mul_w32(C z) {
     }
 }
 
+// cos / sin of 2 pi K / 32 as compile-time constants (K < 16)
+template <int K> struct W32 {
+    static constexpr double c[16] = {1.0, 0.98078528040323044912618223613424, 0.92387953251128675612818318939679,
+                                     0.83146961230254523707878837761791, 0.70710678118654752440084436210485,
+                                     0.55557023301960222474283081394853, 0.38268343236508977172845998403040,
+                                     0.19509032201612826784828486847702, 0.0, -0.19509032201612826784828486847702,
+                                     -0.38268343236508977172845998403040, -0.55557023301960222474283081394853,
+                                     -0.70710678118654752440084436210485, -0.83146961230254523707878837761791,
+                                     -0.92387953251128675612818318939679, -0.98078528040323044912618223613424};
+    static constexpr double s[16] = {0.0, 0.19509032201612826784828486847702, 0.38268343236508977172845998403040,
+                                     0.55557023301960222474283081394853, 0.70710678118654752440084436210485,
+                                     0.83146961230254523707878837761791, 0.92387953251128675612818318939679,
+                                     0.98078528040323044912618223613424, 1.0, 0.98078528040323044912618223613424,
+                                     0.92387953251128675612818318939679, 0.83146961230254523707878837761791,
+                                     0.70710678118654752440084436210485, 0.55557023301960222474283081394853,
+                                     0.38268343236508977172845998403040, 0.19509032201612826784828486847702};
+    static constexpr double cosv = c[K], sinv = s[K];
+};
+
+// X[K] = E[K] + W32^K O[K],  X[K + 16] = E[K] - W32^K O[K]: the twiddle is folded into the butterfly (bfly_w, 6 fused
+// operations instead of 4 + 4); K = 0 and K = 8 (W = -i) need no multiplication at all
 template <typename C, int K> __device__ __forceinline__ void dft32_combine(C (&v)[32], const C (&e)[16], const C (&o)[16]) {
+    typedef typename real_of<C>::type S;
     if constexpr (K < 16) {
         constexpr int p = outpos<16>(K);
+#ifdef FMB_PLAIN_BUTTERFLIES
         const C t = mul_w32<K>(o[p]);
         v[K] = cadd(e[p], t);
         v[K + 16] = csub(e[p], t);
+#else
+        if constexpr (K == 0) { v[0] = cadd(e[p], o[p]); v[16] = csub(e[p], o[p]); }
+        else if constexpr (K == 8) {
+            v[8] = mk<C>(e[p].x + o[p].y, e[p].y - o[p].x);
+            v[24] = mk<C>(e[p].x - o[p].y, e[p].y + o[p].x);
+        } else bfly_w(e[p], o[p], (S)W32<K>::cosv, (S)-W32<K>::sinv, v[K], v[K + 16]);
+#endif
         dft32_combine<C, K + 1>(v, e, o);
     }
 }
@@ -99,7 +129,10 @@ template <typename C> __device__ __forceinline__ void dft32_upper_zero(C (&v)[32
 template <typename C, int K> __device__ __forceinline__ void dft32_combine_lower(C (&v)[32], const C (&e)[16], const C (&o)[16]) {
     if constexpr (K < 16) {
         constexpr int p = outpos<16>(K);
-        v[K] = cadd(e[p], mul_w32<K>(o[p]));
+        typedef typename real_of<C>::type S;
+        if constexpr (K == 0) v[0] = cadd(e[p], o[p]);
+        else if constexpr (K == 8) v[8] = mk<C>(e[p].x + o[p].y, e[p].y - o[p].x);
+        else v[K] = add_w(e[p], o[p], (S)W32<K>::cosv, (S)-W32<K>::sinv);
         dft32_combine_lower<C, K + 1>(v, e, o);
     }
 }
