@@ -136,6 +136,27 @@ template <typename C> FMB_HD void dft8(C *v) {
 // radix 16: r = 4*r1 + r0, q = k0 + 4*k1; X[k0 + 4 k1] = sum_{r0} W16^{r0 k0} W4^{r0 k1} [sum_{r1} v[4 r1 + r0] W4^{r1 k0}]
 // The twiddles W16^{r0 k0} between the two levels are folded into the second level's butterflies (dft4_tw): 154 instead of
 // 164 operations.  -DFMB_PLAIN_BUTTERFLIES restores the multiply-then-butterfly form of round 1.
+// second level of dft16 (the first level - four dft4 over v[r0], v[4 + r0], v[8 + r0], v[12 + r0] - is done)
+template <typename C> FMB_HD void dft16_level2(C *v) {
+    typedef typename real_of<C>::type S;
+    const S h = (S)0.70710678118654752440084436210485;
+    const S c1 = (S)0.92387953251128675612818318939679;   // cos(pi/8)
+    const S s1 = (S)0.38268343236508977172845998403040;   // sin(pi/8)
+    dft4(v[0], v[1], v[2], v[3]);
+    dft4_tw(v[4], v[5], v[6], v[7], c1, -s1, h, -h, s1, -c1);                       // k0 = 1: W16^1, W16^2, W16^3
+    dft4_tw_mi(v[8], v[9], v[10], v[11], h, -h, -h, -h);                            // k0 = 2: W16^2, W16^4 = -i, W16^6
+    dft4_tw(v[12], v[13], v[14], v[15], s1, -c1, -h, -h, -c1, s1);                  // k0 = 3: W16^3, W16^6, W16^9
+}
+// radix-4 butterfly whose FOUR inputs carry run-time twiddles w0 .. w3 (a stage twiddle, a spectrum value, ...):
+// 28 operations instead of 16 (four complex multiplications) + 16
+template <typename C> FMB_HD void dft4_tw4(C &v0, C &v1, C &v2, C &v3, C w0, C w1, C w2, C w3) {
+    C t0, t1, t2, d;
+    bfly_ww(v0, v2, w0.x, w0.y, w2.x, w2.y, t0, t1);
+    bfly_ww(v1, v3, w1.x, w1.y, w3.x, w3.y, t2, d);
+    v0 = cadd(t0, t2); v2 = csub(t0, t2);
+    v1 = mk<C>(t1.x + d.y, t1.y - d.x);
+    v3 = mk<C>(t1.x - d.y, t1.y + d.x);
+}
 template <typename C> FMB_HD void dft16(C *v) {
     typedef typename real_of<C>::type S;
     const S h = (S)0.70710678118654752440084436210485;
@@ -144,10 +165,8 @@ template <typename C> FMB_HD void dft16(C *v) {
 #pragma unroll
     for (int r0 = 0; r0 < 4; ++r0) dft4(v[r0], v[4 + r0], v[8 + r0], v[12 + r0]);   // y[r0][k0] at v[4*k0 + r0]
 #ifndef FMB_PLAIN_BUTTERFLIES
-    dft4(v[0], v[1], v[2], v[3]);
-    dft4_tw(v[4], v[5], v[6], v[7], c1, -s1, h, -h, s1, -c1);                       // k0 = 1: W16^1, W16^2, W16^3
-    dft4_tw_mi(v[8], v[9], v[10], v[11], h, -h, -h, -h);                            // k0 = 2: W16^2, W16^4 = -i, W16^6
-    dft4_tw(v[12], v[13], v[14], v[15], s1, -c1, -h, -h, -c1, s1);                  // k0 = 3: W16^3, W16^6, W16^9
+    dft16_level2(v);
+    (void)h; (void)c1; (void)s1;
 #else
     // twiddles W16^{r0*k0} on v[4*k0 + r0]
     C a;

@@ -153,6 +153,29 @@ __device__ __forceinline__ CPair<float2> ldg_pair_ordered(const CPair<float2> *p
     return r;
 }
 
+// Second radix-32 stage of a 1024-point transform: dft32 of v[m] * W_1024^{jb m}.  The 31 stage twiddles are not multiplied
+// in beforehand (124 operations) but ride on the first butterfly level of the two 16-point sub-transforms (dft4_tw4:
+// 4 operations less per radix-4 butterfly, 32 per call): the four pairs {W^{jb 2p}, W^{jb (2p+1)}}, p = r0, 4 + r0, 8 + r0,
+// 12 + r0, that the r0-th butterflies of the even and the odd sub-transform need are loaded right before them.
+// `tp` = table + jb (pairs 32 apart).  LOWER: outputs q >= 16 are not needed.
+template <typename C, bool LOWER = false> __device__ __forceinline__ void dft32_stage_tw(C (&v)[32], const CPair<C> *tp) {
+    C e[16], o[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { e[r] = v[2 * r]; o[r] = v[2 * r + 1]; }
+#pragma unroll
+    for (int r0 = 0; r0 < 4; ++r0) {
+        const CPair<C> w0 = ldg_pair_ordered(tp + r0 * 32), w1 = ldg_pair_ordered(tp + (4 + r0) * 32),
+                       w2 = ldg_pair_ordered(tp + (8 + r0) * 32), w3 = ldg_pair_ordered(tp + (12 + r0) * 32);
+        if (r0 == 0) dft4_tw(e[0], e[4], e[8], e[12], w1.a.x, w1.a.y, w2.a.x, w2.a.y, w3.a.x, w3.a.y);     // m = 0: twiddle 1
+        else dft4_tw4(e[r0], e[4 + r0], e[8 + r0], e[12 + r0], w0.a, w1.a, w2.a, w3.a);
+        dft4_tw4(o[r0], o[4 + r0], o[8 + r0], o[12 + r0], w0.b, w1.b, w2.b, w3.b);
+    }
+    dft16_level2(e);
+    dft16_level2(o);
+    if constexpr (LOWER) dft32_combine_lower<C, 0>(v, e, o);
+    else dft32_combine<C, 0>(v, e, o);
+}
+
 // dft32 whose odd inputs are prepared by `prep_odd()` only after the even half has been transformed: the middle pass
 // uses it to overlap the latency of the second half of its spectrum loads with sixteen-point butterflies
 template <typename C, typename PrepOdd> __device__ __forceinline__ void dft32_late_odd(C (&v)[32], PrepOdd prep_odd) {
@@ -254,8 +277,10 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
         const unsigned i = i0 + t;
         const C *src = a.in + (long long)col * a.in_cs + (LOAD_T ? (int)i + jb * 1024 : (int)i * 1024 + jb);
         constexpr int fstep = 32 * 1024;
+#ifdef FMB_PLAIN_BUTTERFLIES
         V32Chain h;
         if (OPT & FO_IN_TWIDDLE) h = v32_chain_init(a, i, jb);
+#endif
         // zero padding: logical row f*in_lf + i*in_li < in_n  <=>  32 m < (number of valid f) - jb, one compare per value
         int flim = 0;
         if (OPT & FO_IN_MASK) {
@@ -285,12 +310,14 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
                     val = (OPT & FO_PRE_CONJ) ? cmulc(val, w) : cmul(val, w);
                 }
             }
+#ifdef FMB_PLAIN_BUTTERFLIES
             if (OPT & FO_IN_TWIDDLE) {
                 // the four-step twiddle of the PREVIOUS pass's output, applied here: the chain arithmetic runs while the
                 // loads are in flight, and the (FP32-bound) middle pass of a convolution is relieved of it
                 val = cmul(val, h.c[m & 3]);
                 if (m + 4 < 32) h.c[m & 3] = cmul(h.c[m & 3], h.s4);
             }
+#endif
             v[m] = val;
         }
     }
@@ -298,6 +325,35 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
     V32_T_MARK(v[0].x + v[31].y + v[16].x + v[15].y);                   // (most) loads have arrived, input-side multiplies done
 #endif
     if constexpr ((OPT & FO_IN_HALF) != 0) dft32_upper_zero(v);
+#ifndef FMB_PLAIN_BUTTERFLIES
+    else if constexpr ((OPT & FO_IN_TWIDDLE) != 0) {
+        // The four-step twiddle W_L^{i (jb + 32 m)} of the PREVIOUS pass's output is applied here (the FP32-bound middle
+        // pass of a convolution is relieved of it), folded into the first butterfly level: the r0-th radix-4 butterflies of
+        // the even / odd sub-transform take inputs m = b + 8 j (b = 2 r0 / 2 r0 + 1, j < 4), i.e. the chain
+        // c_b (s^8)^j with c_b = W^{i jb} s^b, s = W_L^{32 i}.  Same number of chain multiplications as applying them one
+        // by one, 32 operations less for the application.
+        const unsigned i = i0 + t;
+        const unsigned ee = i * (unsigned)jb;
+        C cb = cmul(__ldg(a.twL + (ee & a.tw_mask)), __ldg(a.twH + (ee >> a.tw_shift)));       // W^{i jb}
+        const C s1 = __ldg(a.twS + i);
+        const C s2 = cmul(s1, s1), s4 = cmul(s2, s2), s8 = cmul(s4, s4);
+        C e[16], o[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) { e[r] = v[2 * r]; o[r] = v[2 * r + 1]; }
+#pragma unroll
+        for (int r0 = 0; r0 < 4; ++r0) {
+            const C w0 = cb, w1 = cmul(w0, s8), w2 = cmul(w1, s8), w3 = cmul(w2, s8);
+            dft4_tw4(e[r0], e[4 + r0], e[8 + r0], e[12 + r0], w0, w1, w2, w3);
+            cb = cmul(cb, s1);
+            const C x0 = cb, x1 = cmul(x0, s8), x2 = cmul(x1, s8), x3 = cmul(x2, s8);
+            dft4_tw4(o[r0], o[4 + r0], o[8 + r0], o[12 + r0], x0, x1, x2, x3);
+            if (r0 < 3) cb = cmul(cb, s1);
+        }
+        dft16_level2(e);
+        dft16_level2(o);
+        dft32_combine<C, 0>(v, e, o);
+    }
+#endif
     else dft32(v);
     V32_T_MARK(v[0].x + v[31].y);                                       // first butterfly done
     auto exchange_store = [&](int jb_, int t_) {
@@ -313,6 +369,7 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
 #pragma unroll
         for (int m = 0; m < 32; ++m) v[m] = sl[33 * m];
         const CPair<C> *tp = tb + jb_;
+#if defined(V32_DEBUG_NOTW) || defined(FMB_PLAIN_BUTTERFLIES)
 #pragma unroll
         for (int p2 = 0; p2 < 16; ++p2) {
 #ifdef V32_DEBUG_NOTW                                                   /* timing experiment only */
@@ -325,6 +382,9 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
         }
         if constexpr ((OPT & FO_OUT_HALF) != 0 && !TWO) dft32_lower_only(v);
         else dft32(v);
+#else
+        dft32_stage_tw<C, (OPT & FO_OUT_HALF) != 0 && !TWO>(v, tp);
+#endif
     };
 
     // last stage output -> global: four-step twiddle W^{i k}, conj, mask, post-multiply
@@ -389,6 +449,7 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
         for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r));
         stage_b(jb, t, tab);
         V32_T_MARK(v[0].x + v[31].y);                                   // first transform done
+#ifdef FMB_PLAIN_BUTTERFLIES
 #pragma unroll
         for (int r = 0; r < 16; ++r) v[2 * r] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r], mh[r]) : cmul(v[2 * r], mh[r]));
 #pragma unroll
@@ -400,6 +461,32 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
             for (int r = 0; r < 16; ++r)
                 v[2 * r + 1] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r + 1], mh[r]) : cmul(v[2 * r + 1], mh[r]));
         });
+#else
+        {
+            // conj(X S) = conj(X) conj(S): the spectrum rides as a twiddle on the first butterfly level of the inverse
+            // transform's first stage (dft4_tw4) instead of 32 separate complex multiplications.  v[q] = position jb + 32 q
+            // is exactly that stage's input - no exchange.  Even half first; the odd half's spectrum values are requested
+            // once the even ones are consumed and arrive during the even half's second level.
+            auto sw = [](C m) { return (OPT & FO_MID_CONJ) ? m : cconj(m); };
+            C e[16], o[16];
+#pragma unroll
+            for (int r = 0; r < 16; ++r) e[r] = cconj(v[2 * r]);
+#pragma unroll
+            for (int r0 = 0; r0 < 4; ++r0)
+                dft4_tw4(e[r0], e[4 + r0], e[8 + r0], e[12 + r0], sw(mh[r0]), sw(mh[4 + r0]), sw(mh[8 + r0]), sw(mh[12 + r0]));
+#pragma unroll
+            for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r + 1));
+            __syncwarp();                                                // every lane has read its stage inputs
+            dft16_level2(e);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) o[r] = cconj(v[2 * r + 1]);
+#pragma unroll
+            for (int r0 = 0; r0 < 4; ++r0)
+                dft4_tw4(o[r0], o[4 + r0], o[8 + r0], o[12 + r0], sw(mh[r0]), sw(mh[4 + r0]), sw(mh[8 + r0]), sw(mh[12 + r0]));
+            dft16_level2(o);
+            dft32_combine<C, 0>(v, e, o);
+        }
+#endif
         V32_T_MARK(v[0].x + v[31].y);                                   // spectrum product + first stage of the second transform
         exchange_store(jb, t);
         v32_sync<!STORE_T>();

@@ -206,13 +206,7 @@ __device__ __forceinline__ void v32p_tile(const FastArgs<float2> &a, float2 *con
 #pragma unroll
         for (int m = 0; m < 32; ++m) v[m] = sl[33 * m];
         const CPair<C> *tp = tb + jb_;
-#pragma unroll
-        for (int p2 = 0; p2 < 16; ++p2) {
-            const CPair<C> w = ldg_pair_ordered(tp + p2 * 32);
-            if (p2 > 0) v[2 * p2] = cmul(v[2 * p2], w.a);
-            v[2 * p2 + 1] = cmul(v[2 * p2 + 1], w.b);
-        }
-        dft32(v);
+        dft32_stage_tw<C, false>(v, tp);           // the same arithmetic as the per-pass kernels (bit-identical outputs)
     };
     auto final_store = [&](int jb_, int t_) {
         const unsigned i = i0 + t_;
@@ -256,16 +250,27 @@ __device__ __forceinline__ void v32p_tile(const FastArgs<float2> &a, float2 *con
 #pragma unroll
         for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r));
         stage_b(jb, t, tab);
+        {
+            // the same arithmetic as v32_pass_kernel's middle pass: the spectrum rides on the first butterfly level
+            auto sw = [](C m) { return (OPT & FO_MID_CONJ) ? m : cconj(m); };
+            C e[16], o[16];
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[2 * r] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r], mh[r]) : cmul(v[2 * r], mh[r]));
+            for (int r = 0; r < 16; ++r) e[r] = cconj(v[2 * r]);
 #pragma unroll
-        for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r + 1));
-        __syncwarp();
-        dft32_late_odd(v, [&]() {
+            for (int r0 = 0; r0 < 4; ++r0)
+                dft4_tw4(e[r0], e[4 + r0], e[8 + r0], e[12 + r0], sw(mh[r0]), sw(mh[4 + r0]), sw(mh[8 + r0]), sw(mh[12 + r0]));
 #pragma unroll
-            for (int r = 0; r < 16; ++r)
-                v[2 * r + 1] = cconj((OPT & FO_MID_CONJ) ? cmulc(v[2 * r + 1], mh[r]) : cmul(v[2 * r + 1], mh[r]));
-        });
+            for (int r = 0; r < 16; ++r) mh[r] = ld_nc_ordered(mp + 32 * (2 * r + 1));
+            __syncwarp();
+            dft16_level2(e);
+#pragma unroll
+            for (int r = 0; r < 16; ++r) o[r] = cconj(v[2 * r + 1]);
+#pragma unroll
+            for (int r0 = 0; r0 < 4; ++r0)
+                dft4_tw4(o[r0], o[4 + r0], o[8 + r0], o[12 + r0], sw(mh[r0]), sw(mh[4 + r0]), sw(mh[8 + r0]), sw(mh[12 + r0]));
+            dft16_level2(o);
+            dft32_combine<C, 0>(v, e, o);
+        }
         {
             C *sl = smem + t * V32_RS + jb * 33;
 #pragma unroll
