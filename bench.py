@@ -510,12 +510,14 @@ def run_ours(args):
         except Exception as e:
             extras['lfsr_circulant_forward_o20_f32'] = {'error': repr(e)}
         del xf
-        # sizes fastmat's planner actually emits that still run the generic run-time-radix kernels (SURVEY appendix B:
-        # 2^a 3^b paddings such as 6144 and 110592; pass lengths below 256): measured, not yet specialised
-        for nn, mm in ((1 << 14, 1024), (6144, 1024), (110592, 256)):
+        # mid sizes: 2^14 / 2^15 (pass length 128) run the specialised passes since round 2; 2^13 (one shared-memory kernel)
+        # and the 2^a 3^b paddings fastmat's planner emits (6144, 110592) still run the generic
+        # run-time-radix kernels: measured, not yet specialised
+        for nn, mm, tag in ((1 << 13, 1024, 'generic_kernel'), (1 << 14, 1024, 'fast_path'), (1 << 15, 1024, 'fast_path'),
+                            (6144, 1024, 'generic_kernel'), (110592, 256, 'generic_kernels')):
             Fs = fm.Fourier(nn)
             xs_ = crandn(nn, mm)
-            rec('fourier_forward_%d_c64_generic_kernels' % nn, lambda: Fs.forward(xs_), mm, 16.0 * nn, k=10, sustain=0)
+            rec('fourier_forward_%d_c64_%s' % (nn, tag), lambda: Fs.forward(xs_), mm, 16.0 * nn, k=10, sustain=0)
             del xs_, Fs
         x16 = crandn(1 << 16, 64).to(torch.complex128)
         F16 = fm.Fourier(1 << 16)

@@ -177,11 +177,12 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
         // butterfly index fastest:  stage 2 (Ns = 16, radix 16) then stage 3 (Ns = 256, radix P2)
         for (int g = 0; g < 2; ++g) {
             const int64_t Rg = shape.g[g].R;
-            if (Rg < 256 || Rg > 4096) continue;
+            if (Rg < 128 || Rg > 4096) continue;
             auto root = unit_root;
             w.clear();
-            for (int p2 = 0; p2 < 8; ++p2)
-                for (int kk = 0; kk < 16; ++kk) { w.push_back(root(kk * 2 * p2, 256)); w.push_back(root(kk * (2 * p2 + 1), 256)); }
+            const int P1 = Rg >= 256 ? 16 : (int)(Rg / 16);         // R = 128: radix 16 then radix 8 (FastPlan<7>)
+            for (int p2 = 0; p2 < P1 / 2; ++p2)
+                for (int kk = 0; kk < 16; ++kk) { w.push_back(root(kk * 2 * p2, 16 * P1)); w.push_back(root(kk * (2 * p2 + 1), 16 * P1)); }
             const int P2 = (int)(Rg / 256);
             for (int p2 = 0; p2 < P2 / 2; ++p2)
                 for (int kk = 0; kk < 256; ++kk) { w.push_back(root((int64_t)kk * 2 * p2, Rg)); w.push_back(root((int64_t)kk * (2 * p2 + 1), Rg)); }
@@ -427,6 +428,8 @@ static const unsigned FV_A_F_ = FO_LOAD_T | FO_TWIDDLE, FV_A_FC_ = FV_A_F_ | FO_
                       FV_C_M_ = FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK, FV_C_MP_ = FV_C_M_ | FO_POST,
                       FV_C_MPC_ = FV_C_MP_ | FO_POST_CONJ, FV_K_AC_ = FV_B_F_ | FO_IN_CONJ, FV_K_B_ = FO_OUT_MASK,
                       FV_K_BC_ = FO_OUT_MASK | FO_OUT_CONJ;
+int launch_fast_f32_L7(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f64_L7(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L8(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L9(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L10(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
@@ -437,12 +440,13 @@ int launch_fast_f64_L9(unsigned opt, const FastArgs<double2> &a, unsigned tiles,
 int launch_fast_f64_L10(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f64_L11(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 
-static bool fast_has(const float2 *, int logr) { return logr >= 8 && logr <= 12; }
-static bool fast_has(const double2 *, int logr) { return logr >= 8 && logr <= 11; }
+static bool fast_has(const float2 *, int logr) { return logr >= 7 && logr <= 12; }
+static bool fast_has(const double2 *, int logr) { return logr >= 7 && logr <= 11; }
 static int fast_logt(const float2 *, int logr) { return (logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr); }
 static int fast_logt(const double2 *, int logr) { return ((logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr)) - 1; }
 static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
     switch (logr) {
+        case 7: return launch_fast_f32_L7(opt, a, tiles, st);
         case 8: return launch_fast_f32_L8(opt, a, tiles, st);
         case 9: return launch_fast_f32_L9(opt, a, tiles, st);
         case 10: return launch_fast_f32_L10(opt, a, tiles, st);
@@ -452,6 +456,7 @@ static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsign
 }
 static int fast_launch(int logr, unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st) {
     switch (logr) {
+        case 7: return launch_fast_f64_L7(opt, a, tiles, st);
         case 8: return launch_fast_f64_L8(opt, a, tiles, st);
         case 9: return launch_fast_f64_L9(opt, a, tiles, st);
         case 10: return launch_fast_f64_L10(opt, a, tiles, st);

@@ -858,3 +858,29 @@ def test_concurrent_host_threads_on_one_plan(fm):
     assert not errs, errs
     for i in range(4):
         assert torch.equal(out[i], ref[i]), i
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('n', [2 ** 14, 2 ** 15])
+def test_pass_length_128_fast_path(fm, orc, n):
+    """2^14 = 128 x 128 and 2^15 = 128 x 256 run the compile-time specialised passes since round 2 (FastPlan<7>: radix 16
+    then radix 8); round 1 sent them to the generic run-time-radix kernel.  Fourier / Circulant / Toeplitz, forward and
+    backward, both precisions, against the oracle."""
+    x = seeded(700 + n % 97, n, 5)
+    c = seeded(701, n)
+    for dt, tol in ((np.complex64, TOL64), (np.complex128, TOL128)):
+        xd = dev(x.astype(dt))
+        nx = np.linalg.norm(x, axis=0).max() * np.log2(n)
+        F = fm.Fourier(n)
+        assert np.abs(F.forward(xd).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        assert np.abs(F.backward(xd).cpu().numpy() - orc.fourier_backward(x)).max() / nx < tol
+        C = fm.Circulant(c.astype(dt))
+        ncn = np.linalg.norm(c) * nx
+        assert np.abs(C.forward(xd).cpu().numpy() - orc.circulant_forward(c, x)).max() / ncn < tol
+        assert np.abs(C.backward(xd).cpu().numpy() - orc.circulant_backward(c, x)).max() / ncn < tol
+    nt = n // 2
+    T = fm.Toeplitz(c[:nt].astype(np.complex64), c[nt:2 * nt - 1].astype(np.complex64))
+    xt = x[:nt]
+    ntn = np.linalg.norm(c) * np.linalg.norm(xt, axis=0).max() * np.log2(n)
+    assert np.abs(T.forward(dev(xt.astype(np.complex64))).cpu().numpy() - orc.toeplitz_forward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < TOL64
+    assert np.abs(T.backward(dev(xt.astype(np.complex64))).cpu().numpy() - orc.toeplitz_backward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < TOL64

@@ -8,6 +8,6 @@ tail -2 gpurun_out/r2_prof_bench.log | cut -c1-300
 FMB_PIPE_STREAMS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:v32 -s 9 -c 3 -f -o gpurun_out/r2_circ_slab64 build/cbench $L circ 64 1 > /dev/null 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:v32p -s 3 -c 1 -f -o gpurun_out/r2_fourier_v32p build/cbench $L fourier 64 1 > /dev/null 2>&1
 FMB_FWHT_PIPE_STREAMS=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fwht -s 6 -c 2 -f -o gpurun_out/r2_hadamard build/cbench $L had 128 1 > /dev/null 2>&1
-CBENCH_PROFILE=1 timeout 300 ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum --clock-control none build/cbench $L circ 1024 1 > gpurun_out/r2_range_circ1024.txt 2>&1
+FMB_V32T=0 CBENCH_PROFILE=1 timeout 300 ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum,lts__t_sectors_srcunit_tex_op_read.sum,lts__t_sectors_srcunit_tex_op_write.sum,lts__t_sector_hit_rate.pct,gpu__time_duration.sum --clock-control none build/cbench $L circ 1024 1 > gpurun_out/r2_range_circ1024.txt 2>&1
 tail -14 gpurun_out/r2_range_circ1024.txt
 ls -la gpurun_out/*.ncu-rep gpurun_out/r2_launches_bench_circulant.csv
