@@ -70,7 +70,7 @@ static void make_radices(int64_t R, PassGeom &g) {
 
 static int64_t pass_limit(const PassGeom &g) { return (int64_t)FMB_MAX_NT * g.min_pnb; }   // R*T <= limit, T >= 1
 
-bool plan_shape(int64_t L, FftShape &s) {
+bool plan_shape(int64_t L, FftShape &s, bool prefer_two) {
     s = FftShape();
     s.L = L;
     if (L < 2) return false;
@@ -80,7 +80,8 @@ bool plan_shape(int64_t L, FftShape &s) {
     if (primes.size() > (size_t)2 * FMB_MAX_STAGES) return false;
     PassGeom g;
     make_radices(L, g);
-    if (L <= pass_limit(g) && (int)g.radix.size() <= FMB_MAX_STAGES && L <= 8192) {
+    if (L <= pass_limit(g) && (int)g.radix.size() <= FMB_MAX_STAGES && L <= 8192 &&
+        !(prefer_two && (L & (L - 1)) == 0 && L > 4096)) {
         s.npass = 1;
         s.g[0] = g;
         return true;
@@ -114,7 +115,14 @@ bool plan_shape(int64_t L, FftShape &s) {
 // ------------------------------------------------------------------------------------------- engine setup
 int ConvEngine::init(int64_t L_, int64_t n_in_, int64_t n_out_, bool two_ffts_) {
     L = L_; n_in = n_in_; n_out = n_out_; two_ffts = two_ffts_;
-    if (!plan_shape(L, shape)) {
+    // 8192 = 64 x 128: two specialised passes over an L2-resident intermediate beat the one generic kernel (5x)
+#ifdef FMB_EMULATE
+    const bool two = false;
+#else
+    static const long single8k = env_long("FMB_SINGLE_8192", 0);
+    const bool two = !single8k;
+#endif
+    if (!plan_shape(L, shape, two)) {
         set_error("FFT length %lld is not directly transformable", (long long)L);
         return FMB_ERR_VALUE;
     }
@@ -172,12 +180,12 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
         int rc = upload_cvec<C>(d.wR[g], w);
         if (rc) return rc;
     }
-    if (shape.npass == 2 && shape.pow2) {
+    if (shape.pow2) {
         // fast path (fft_fast.cuh): per-stage twiddle tables of a pass length R = 16 * 16 * P2, pairs (r = 2p, 2p+1),
         // butterfly index fastest:  stage 2 (Ns = 16, radix 16) then stage 3 (Ns = 256, radix P2)
-        for (int g = 0; g < 2; ++g) {
+        for (int g = 0; g < shape.npass; ++g) {
             const int64_t Rg = shape.g[g].R;
-            if (Rg < 128 || Rg > 4096) continue;
+            if (Rg < 64 || Rg > 4096) continue;
             auto root = unit_root;
             w.clear();
             const int P1 = Rg >= 256 ? 16 : (int)(Rg / 16);         // R = 128: radix 16 then radix 8 (FastPlan<7>)
@@ -188,7 +196,7 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
                 for (int kk = 0; kk < 256; ++kk) { w.push_back(root((int64_t)kk * 2 * p2, Rg)); w.push_back(root((int64_t)kk * (2 * p2 + 1), Rg)); }
             int rc = upload_cvec<C>(d.twF[g], w);
             if (rc) return rc;
-            if (Rg == 1024) {
+            if (Rg == 1024 && shape.npass == 2) {
                 // 32-values-per-thread passes (fft_v32.cuh): second-stage twiddles {W_1024^{kk 2p}, W_1024^{kk (2p+1)}} at
                 // [p * 32 + kk], stored twice (see v32_pass_kernel), and the four-step step factor W_L^{32 i}
                 w.clear();
@@ -427,7 +435,10 @@ static const unsigned FV_A_F_ = FO_LOAD_T | FO_TWIDDLE, FV_A_FC_ = FV_A_F_ | FO_
                       FV_BM_ = FO_LOAD_T | FO_STORE_T | FO_TWO_FFTS | FO_TWIDDLE, FV_BMC_ = FV_BM_ | FO_MID_CONJ,
                       FV_C_M_ = FO_STORE_T | FO_OUT_CONJ | FO_OUT_MASK, FV_C_MP_ = FV_C_M_ | FO_POST,
                       FV_C_MPC_ = FV_C_MP_ | FO_POST_CONJ, FV_K_AC_ = FV_B_F_ | FO_IN_CONJ, FV_K_B_ = FO_OUT_MASK,
-                      FV_K_BC_ = FO_OUT_MASK | FO_OUT_CONJ;
+                      FV_K_BC_ = FO_OUT_MASK | FO_OUT_CONJ, FV_1_FC_ = FO_IN_CONJ | FO_OUT_CONJ | FO_OUT_MASK,
+                      FV_1_M_ = FO_TWO_FFTS | FO_IN_MASK | FO_OUT_CONJ | FO_OUT_MASK, FV_1_MC_ = FV_1_M_ | FO_MID_CONJ;
+int launch_fast_f32_L6(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
+int launch_fast_f64_L6(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L7(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f64_L7(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f32_L8(unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st);
@@ -440,12 +451,13 @@ int launch_fast_f64_L9(unsigned opt, const FastArgs<double2> &a, unsigned tiles,
 int launch_fast_f64_L10(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 int launch_fast_f64_L11(unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st);
 
-static bool fast_has(const float2 *, int logr) { return logr >= 7 && logr <= 12; }
-static bool fast_has(const double2 *, int logr) { return logr >= 7 && logr <= 11; }
+static bool fast_has(const float2 *, int logr) { return logr >= 6 && logr <= 12; }
+static bool fast_has(const double2 *, int logr) { return logr >= 6 && logr <= 11; }
 static int fast_logt(const float2 *, int logr) { return (logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr); }
 static int fast_logt(const double2 *, int logr) { return ((logr <= 9) ? (12 - logr) : (FMB_FAST_TILE_LOG2 - logr)) - 1; }
 static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsigned tiles, cudaStream_t st) {
     switch (logr) {
+        case 6: return launch_fast_f32_L6(opt, a, tiles, st);
         case 7: return launch_fast_f32_L7(opt, a, tiles, st);
         case 8: return launch_fast_f32_L8(opt, a, tiles, st);
         case 9: return launch_fast_f32_L9(opt, a, tiles, st);
@@ -456,6 +468,7 @@ static int fast_launch(int logr, unsigned opt, const FastArgs<float2> &a, unsign
 }
 static int fast_launch(int logr, unsigned opt, const FastArgs<double2> &a, unsigned tiles, cudaStream_t st) {
     switch (logr) {
+        case 6: return launch_fast_f64_L6(opt, a, tiles, st);
         case 7: return launch_fast_f64_L7(opt, a, tiles, st);
         case 8: return launch_fast_f64_L8(opt, a, tiles, st);
         case 9: return launch_fast_f64_L9(opt, a, tiles, st);
@@ -473,6 +486,42 @@ template <typename C> bool ConvEngine::fast_ok(int64_t xrs, int64_t yrs, bool in
     if (off || !shape.pow2 || shape.npass != 2 || in_real || xrs != 1 || yrs != 1) return false;
     if (L >= ((int64_t)1 << 30)) return false;
     return fast_has((const C *)nullptr, ilog2_host(shape.g[0].R)) && fast_has((const C *)nullptr, ilog2_host(shape.g[1].R));
+#endif
+}
+
+// Whole transform in ONE kernel (power-of-two L of 128 ... 4096, column-major operands): a line of the specialised pass
+// kernel is a column of the operand, a tile is T neighbouring columns.  Fourier is one transform per line; Circulant and
+// Toeplitz are FFT -> spectrum -> conj -> FFT -> conj without leaving shared memory, the Toeplitz zero padding being the
+// load mask and its cropping the store mask.  Handles the first M - M % T columns; returns how many in `done`.
+template <typename C>
+int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M,
+                                int64_t &done, cudaStream_t st) const {
+    done = 0;
+#ifdef FMB_EMULATE
+    return FMB_OK;
+#else
+    static const long off = env_long("FMB_NO_FAST", 0), off1 = env_long("FMB_NO_FAST1", 0);
+    const int l = ilog2_host(L);
+    if (off || off1 || !shape.pow2 || shape.npass != 1 || !fast_has((const C *)nullptr, l)) return FMB_OK;
+    if (!pre.empty() || !post.empty() || (two_ffts && mid.empty())) return FMB_OK;
+    const int lt = fast_logt((const C *)nullptr, l);
+    const int64_t T = (int64_t)1 << lt, Mf = M & ~(T - 1);
+    if (Mf == 0 || xcs * T >= ((int64_t)1 << 31) || ycs * T >= ((int64_t)1 << 31) || (Mf >> lt) >= ((int64_t)1 << 31)) return FMB_OK;
+    const bool bwd = direction == FMB_BACKWARD;
+    FastArgs<C> a;
+    memset(&a, 0, sizeof(a));
+    a.ncols = (int)Mf;
+    a.in = (const C *)x; a.in_cs = T * xcs; a.in_fs = 1; a.in_is = (int)xcs;
+    a.out = (C *)y; a.out_cs = T * ycs; a.out_ks = 1; a.out_is = (int)ycs;
+    a.I = (int)T; a.logI = lt;
+    a.in_n = (int)(bwd ? n_out : n_in); a.in_lf = 1; a.in_li = 0;
+    a.out_n = (int)(bwd ? n_in : n_out); a.out_lk = 1; a.out_li = 0;
+    a.mid = (const C *)d.mid.p; a.mid_is = 0;
+    a.tw = (const C *)d.twF[0].p;
+    const unsigned opt = two_ffts ? (bwd ? FV_1_MC_ : FV_1_M_) : (bwd ? FV_1_FC_ : FV_K_B_);
+    int rc = fast_launch(l, opt, a, (unsigned)(Mf >> lt), st);
+    if (rc == FMB_OK) done = Mf;
+    return rc;
 #endif
 }
 
@@ -955,6 +1004,13 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
     const bool pow2 = shape.pow2;
 
     if (shape.npass == 1) {
+        if (!in_real && xrs == 1 && yrs == 1) {
+            // specialised single-kernel route for whole tiles of columns; a ragged tail takes the generic kernel below
+            int64_t done = 0;
+            if ((rc = run_single_fast<C>(d, direction, x, xcs, y, ycs, M, done, st))) return rc;
+            if (done == M) return FMB_OK;
+            x = (const C *)x + done * xcs; y = (C *)y + done * ycs; M -= done;
+        }
         PassParams<C> p = blank_params<C>();
         p.two_ffts = two_ffts;
         p.lines_total = M; p.I = 1; p.ncols = M; p.line_c_fastest = 0;

@@ -28,7 +28,7 @@ struct FftShape {
 };
 
 // true if L can be transformed directly (all prime factors <= 13 and it splits into <= 2 shared-memory passes)
-bool plan_shape(int64_t L, FftShape &shape);
+bool plan_shape(int64_t L, FftShape &shape, bool prefer_two = false);   // prefer_two: 8192 as 64 x 128 instead of one pass
 int64_t next_pow2(int64_t v);
 
 struct ConvEngine {
@@ -62,6 +62,8 @@ struct ConvEngine {
    private:
     template <typename C> int ensure_dev(Dev &d) const;
     template <typename C> bool fast_ok(int64_t xrs, int64_t yrs, bool in_real) const;
+    template <typename C>
+    int run_single_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, int64_t &done, cudaStream_t st) const;
     template <typename C>
     int run_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const;
     bool v32_ok(size_t csize) const;

@@ -17,6 +17,7 @@
 namespace fmb {
 
 template <int LOGR> struct FastPlan;      // radix plan: first stage radix 16 (Ns = 1), then 16s, then the remainder
+template <> struct FastPlan<6>  { static constexpr int S = 2; static constexpr int P0 = 16, P1 = 4,  P2 = 1; };
 template <> struct FastPlan<7>  { static constexpr int S = 2; static constexpr int P0 = 16, P1 = 8,  P2 = 1; };
 template <> struct FastPlan<8>  { static constexpr int S = 2; static constexpr int P0 = 16, P1 = 16, P2 = 1; };
 template <> struct FastPlan<9>  { static constexpr int S = 3; static constexpr int P0 = 16, P1 = 16, P2 = 2; };
@@ -239,7 +240,7 @@ __device__ __forceinline__ void fast_pass_part(const FastArgs<C> &a, unsigned ti
 #pragma unroll
         for (int m = 0; m < 16; ++m) v[m] = b[ROWS * m + (ROWS * m >> 4)];      // ROWS*m is a multiple of 16 when ROWS >= 16
     };
-    static_assert(ROWS % 16 == 0 || ROWS == 8, "row count must keep the pad offsets separable");
+    static_assert(ROWS % 16 == 0 || ROWS == 8 || ROWS == 4, "row count must keep the pad offsets separable");
     auto load16g = [&](const C *sl, int jb_) {
         if constexpr (ROWS % 16 == 0) load16(sl, jb_);
         else {

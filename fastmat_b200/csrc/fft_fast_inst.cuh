@@ -1,4 +1,4 @@
-// One translation unit per (precision, log2 R) instantiates the twelve pass variants of the fast path.
+// One translation unit per (precision, log2 R) instantiates the pass variants of the fast path.
 #pragma once
 #include "common.h"
 #include "fft_fast.cuh"
@@ -21,6 +21,10 @@ constexpr unsigned FV_C_MPC = FV_C_MP | FO_POST_CONJ;
 constexpr unsigned FV_K_AC = FV_B_F | FO_IN_CONJ;                                    // Kron: first pass of the backward
 constexpr unsigned FV_K_B = FO_OUT_MASK;                                             // Kron: second pass (rows contiguous)
 constexpr unsigned FV_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
+// whole transforms in one kernel (L <= 4096: a line is a column of the operand, see fft_engine.cu: run_single_fast)
+constexpr unsigned FV_1_FC = FO_IN_CONJ | FO_OUT_CONJ | FO_OUT_MASK;                  // backward Fourier (forward: FV_K_B)
+constexpr unsigned FV_1_M = FO_TWO_FFTS | FO_IN_MASK | FO_OUT_CONJ | FO_OUT_MASK;     // Circulant / Toeplitz on chip
+constexpr unsigned FV_1_MC = FV_1_M | FO_MID_CONJ;
 
 template <typename C, int LOGR, unsigned OPT>
 int launch_fast_variant(const FastArgs<C> &a, unsigned tiles, cudaStream_t st) {
@@ -54,6 +58,9 @@ template <typename C, int LOGR> int launch_fast_logr(unsigned opt, const FastArg
         case FV_K_AC: return launch_fast_variant<C, LOGR, FV_K_AC>(a, tiles, st);
         case FV_K_B: return launch_fast_variant<C, LOGR, FV_K_B>(a, tiles, st);
         case FV_K_BC: return launch_fast_variant<C, LOGR, FV_K_BC>(a, tiles, st);
+        case FV_1_FC: return launch_fast_variant<C, LOGR, FV_1_FC>(a, tiles, st);
+        case FV_1_M: return launch_fast_variant<C, LOGR, FV_1_M>(a, tiles, st);
+        case FV_1_MC: return launch_fast_variant<C, LOGR, FV_1_MC>(a, tiles, st);
         default: set_error("fast path: unknown pass variant %u", opt); return FMB_ERR_NOTIMPL;
     }
 }

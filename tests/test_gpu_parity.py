@@ -861,9 +861,9 @@ def test_concurrent_host_threads_on_one_plan(fm):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('n', [2 ** 14, 2 ** 15])
+@pytest.mark.parametrize('n', [2 ** 13, 2 ** 14, 2 ** 15])
 def test_pass_length_128_fast_path(fm, orc, n):
-    """2^14 = 128 x 128 and 2^15 = 128 x 256 run the compile-time specialised passes since round 2 (FastPlan<7>: radix 16
+    """2^13 = 64 x 128 (FastPlan<6>: radix 16 then radix 4), 2^14 = 128 x 128 and 2^15 = 128 x 256 run the compile-time specialised passes since round 2 (FastPlan<7>: radix 16
     then radix 8); round 1 sent them to the generic run-time-radix kernel.  Fourier / Circulant / Toeplitz, forward and
     backward, both precisions, against the oracle."""
     x = seeded(700 + n % 97, n, 5)
@@ -884,3 +884,67 @@ def test_pass_length_128_fast_path(fm, orc, n):
     ntn = np.linalg.norm(c) * np.linalg.norm(xt, axis=0).max() * np.log2(n)
     assert np.abs(T.forward(dev(xt.astype(np.complex64))).cpu().numpy() - orc.toeplitz_forward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < TOL64
     assert np.abs(T.backward(dev(xt.astype(np.complex64))).cpu().numpy() - orc.toeplitz_backward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < TOL64
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [64, 128, 256, 512, 1024, 2048, 4096])
+def test_single_kernel_fast_path(fm, orc, n):
+    """Power-of-two lengths 128 ... 4096 run as ONE specialised kernel per apply (fft_engine.cu: run_single_fast): a line
+    of the pass kernel is a column of the operand; Circulant / Toeplitz do FFT -> spectrum -> FFT on chip with the zero
+    padding as load mask.  Column counts that are not a multiple of the tile (the tail takes the generic kernel), a
+    strided (non-contiguous) column batch, both precisions and both directions, against the oracle."""
+    cols = 3 * 64 + 5
+    x = seeded(900 + n % 89, n, cols)
+    c = seeded(901, n)
+    for dt, tol in ((np.complex64, TOL64), (np.complex128, TOL128)):
+        xd = dev(x.astype(dt))
+        nx = np.linalg.norm(x, axis=0).max() * np.log2(n)
+        F = fm.Fourier(n)
+        assert np.abs(F.forward(xd).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        assert np.abs(F.backward(xd).cpu().numpy() - orc.fourier_backward(x)).max() / nx < tol
+        C = fm.Circulant(c.astype(dt))
+        ncn = np.linalg.norm(c) * nx
+        assert np.abs(C.forward(xd).cpu().numpy() - orc.circulant_forward(c, x)).max() / ncn < tol
+        assert np.abs(C.backward(xd).cpu().numpy() - orc.circulant_backward(c, x)).max() / ncn < tol
+        # every second column of a wider column-major batch: column stride 2 n
+        wide = dev(np.repeat(x.astype(dt), 2, axis=1))
+        assert np.abs(F.forward(wide[:, ::2]).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        # Toeplitz of order n/2 + 1 ... pads to n: rows beyond the order are masked on load and cropped on store
+        nt = n // 2
+        T = fm.Toeplitz(c[:nt].astype(dt), c[nt:2 * nt - 1].astype(dt))
+        xt = x[:nt]
+        ntn = np.linalg.norm(c) * np.linalg.norm(xt, axis=0).max() * np.log2(n)
+        assert np.abs(T.forward(dev(xt.astype(dt))).cpu().numpy() - orc.toeplitz_forward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
+        assert np.abs(T.backward(dev(xt.astype(dt))).cpu().numpy() - orc.toeplitz_backward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
+    # the two routes agree to rounding on the same input (same algorithm, different radix plan)
+    import os
+    import subprocess
+    import sys
+    code = ("import numpy as np, torch, fastmat_b200 as fm\n"
+            "rng = np.random.default_rng(5); n = %d\n"
+            "x = torch.from_numpy((rng.standard_normal((64, n)) + 1j * rng.standard_normal((64, n))).astype(np.complex64)).cuda().t()\n"
+            "y = fm.Fourier(n).forward(x)\n"
+            "print(float(torch.linalg.vector_norm(y - torch.fft.fft(x.to(torch.complex128), dim=0).to(torch.complex64)) / torch.linalg.vector_norm(y)))\n" % n)
+    errs = []
+    for flag in ("0", "1"):
+        env = dict(os.environ, FMB_NO_FAST1=flag)
+        out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300,
+                             cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        assert out.returncode == 0, out.stderr[-2000:]
+        errs.append(float(out.stdout.strip().splitlines()[-1]))
+    assert max(errs) < 1e-6, errs
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dims", [(64, 64), (64, 128), (256, 64)])
+def test_kron_fourier_pass_length_64(fm, orc, dims):
+    """Kron(Fourier(a), Fourier(b)) with a factor of 64 runs the specialised passes (FastPlan<6>) instead of the generic
+    kernel; forward and backward, both precisions, against the N-D FFT of the oracle."""
+    n = dims[0] * dims[1]
+    x = seeded(950 + dims[0], n, 7)
+    K = fm.Kron(fm.Fourier(dims[0]), fm.Fourier(dims[1]))
+    nx = np.linalg.norm(x, axis=0).max() * np.log2(n)
+    for dt, tol in ((np.complex64, TOL64), (np.complex128, TOL128)):
+        xd = dev(x.astype(dt))
+        assert np.abs(K.forward(xd).cpu().numpy() - orc.kron_fourier_forward(dims, x)).max() / nx < tol
+        assert np.abs(K.backward(xd).cpu().numpy() - orc.kron_fourier_backward(dims, x)).max() / nx < tol
