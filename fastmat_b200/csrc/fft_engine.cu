@@ -277,9 +277,11 @@ int ConvEngine::slab_cols(int64_t M, size_t csize) const {
 }
 
 int transpose_apply(const void *in, int64_t lda, void *out, int64_t ldb, int64_t ni, int64_t nj, size_t esize, cudaStream_t st);
-static int64_t rm_chunk() {
+// columns per transposed chunk of the row-major route: FMB_RM_CHUNK (32) columns of 2^20 rows, and as many more of a
+// shorter transform as make the same 256 MiB (chunks of 32 short columns would be launch bound)
+static int64_t rm_chunk(int64_t L = (int64_t)1 << 20) {
     static const long v = env_long("FMB_RM_CHUNK", 32);
-    return v;
+    return L >= ((int64_t)1 << 20) ? (int64_t)v : (int64_t)v * (((int64_t)1 << 20) / L);
 }
 
 // scratch of an apply: the column-major requirement, or - if larger - what the chunked row-major route needs (a chunk's
@@ -287,7 +289,7 @@ static int64_t rm_chunk() {
 int64_t ConvEngine::workspace_bytes(int64_t M, size_t csize) const {
     const int64_t cm = workspace_bytes_cm(M, csize);
     if (shape.npass != 2 || !shape.pow2 || rm_chunk() <= 0 || M < 2) return cm;
-    const int64_t tc = std::min<int64_t>(M, rm_chunk());
+    const int64_t tc = std::min<int64_t>(M, rm_chunk(L));
     return std::max(cm, workspace_bytes_cm(tc, csize) + (n_in + n_out) * tc * (int64_t)csize);
 }
 
@@ -492,10 +494,12 @@ template <typename C> bool ConvEngine::fast_ok(int64_t xrs, int64_t yrs, bool in
 // Whole transform in ONE kernel (power-of-two L of 128 ... 4096, column-major operands): a line of the specialised pass
 // kernel is a column of the operand, a tile is T neighbouring columns.  Fourier is one transform per line; Circulant and
 // Toeplitz are FFT -> spectrum -> conj -> FFT -> conj without leaving shared memory, the Toeplitz zero padding being the
-// load mask and its cropping the store mask.  Handles the first M - M % T columns; returns how many in `done`.
+// load mask and its cropping the store mask.  Row-major operands (batch contiguous) use the line-fastest thread order:
+// the T columns of a tile are the contiguous direction (8 T bytes per row: full 32-byte sectors from T = 4, i.e. up to
+// L = 2048).  Handles the first M - M % T columns; returns how many in `done`.
 template <typename C>
-int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M,
-                                int64_t &done, cudaStream_t st) const {
+int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
+                                int64_t ycs, int64_t M, int64_t &done, cudaStream_t st) const {
     done = 0;
 #ifdef FMB_EMULATE
     return FMB_OK;
@@ -506,19 +510,29 @@ int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xc
     if (!pre.empty() || !post.empty() || (two_ffts && mid.empty())) return FMB_OK;
     const int lt = fast_logt((const C *)nullptr, l);
     const int64_t T = (int64_t)1 << lt, Mf = M & ~(T - 1);
-    if (Mf == 0 || xcs * T >= ((int64_t)1 << 31) || ycs * T >= ((int64_t)1 << 31) || (Mf >> lt) >= ((int64_t)1 << 31)) return FMB_OK;
+    const bool rm = !(xrs == 1 && yrs == 1);
+    if (rm && !(xcs == 1 && ycs == 1)) return FMB_OK;
+    const int64_t lim = (int64_t)1 << 30;
+    if (Mf == 0 || Mf >= lim || xcs * T >= lim || ycs * T >= lim || xrs >= lim || yrs >= lim) return FMB_OK;
     const bool bwd = direction == FMB_BACKWARD;
     FastArgs<C> a;
     memset(&a, 0, sizeof(a));
     a.ncols = (int)Mf;
-    a.in = (const C *)x; a.in_cs = T * xcs; a.in_fs = 1; a.in_is = (int)xcs;
-    a.out = (C *)y; a.out_cs = T * ycs; a.out_ks = 1; a.out_is = (int)ycs;
-    a.I = (int)T; a.logI = lt;
+    a.in = (const C *)x; a.out = (C *)y;
+    if (!rm) {
+        a.in_cs = T * xcs; a.in_fs = 1; a.in_is = (int)xcs;
+        a.out_cs = T * ycs; a.out_ks = 1; a.out_is = (int)ycs;
+        a.I = (int)T; a.logI = lt;
+    } else {
+        a.in_cs = 0; a.in_fs = (int)xrs; a.in_is = 1;                  // one "column group" holding every line
+        a.out_cs = 0; a.out_ks = (int)yrs; a.out_is = 1;
+        a.I = (int)lim; a.logI = 30;
+    }
     a.in_n = (int)(bwd ? n_out : n_in); a.in_lf = 1; a.in_li = 0;
     a.out_n = (int)(bwd ? n_in : n_out); a.out_lk = 1; a.out_li = 0;
     a.mid = (const C *)d.mid.p; a.mid_is = 0;
     a.tw = (const C *)d.twF[0].p;
-    const unsigned opt = two_ffts ? (bwd ? FV_1_MC_ : FV_1_M_) : (bwd ? FV_1_FC_ : FV_K_B_);
+    const unsigned opt = (two_ffts ? (bwd ? FV_1_MC_ : FV_1_M_) : (bwd ? FV_1_FC_ : FV_K_B_)) | (rm ? (FO_LOAD_T | FO_STORE_T) : 0u);
     int rc = fast_launch(l, opt, a, (unsigned)(Mf >> lt), st);
     if (rc == FMB_OK) done = Mf;
     return rc;
@@ -1004,10 +1018,10 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
     const bool pow2 = shape.pow2;
 
     if (shape.npass == 1) {
-        if (!in_real && xrs == 1 && yrs == 1) {
+        if (!in_real) {
             // specialised single-kernel route for whole tiles of columns; a ragged tail takes the generic kernel below
             int64_t done = 0;
-            if ((rc = run_single_fast<C>(d, direction, x, xcs, y, ycs, M, done, st))) return rc;
+            if ((rc = run_single_fast<C>(d, direction, x, xrs, xcs, y, yrs, ycs, M, done, st))) return rc;
             if (done == M) return FMB_OK;
             x = (const C *)x + done * xcs; y = (C *)y + done * ycs; M -= done;
         }
@@ -1029,7 +1043,7 @@ int ConvEngine::run_t(Dev &d, int direction, const void *x, int64_t xrs, int64_t
     // FMB_RM_CHUNK columns are transposed into the column-major layout, pushed through the fast path and transposed back
     // (the generic strided kernel below needs 5-9x the time of the fast path; two extra sweeps cost ~0.7x).
     if (rowmajor && ycs == 1 && !in_real && fast_ok<C>(1, 1, false) && rm_chunk() > 0) {
-        const int64_t tc = std::min<int64_t>(M, rm_chunk());
+        const int64_t tc = std::min<int64_t>(M, rm_chunk(L));
         const int64_t inner = workspace_bytes_cm(tc, sizeof(C));
         const int64_t need = inner + (rows_in + rows_out) * tc * (int64_t)sizeof(C);
         if (ws == nullptr || ws_bytes < need) { set_error("workspace too small: need %lld bytes", (long long)need); return FMB_ERR_WORKSPACE; }

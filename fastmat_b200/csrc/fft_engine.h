@@ -63,7 +63,8 @@ struct ConvEngine {
     template <typename C> int ensure_dev(Dev &d) const;
     template <typename C> bool fast_ok(int64_t xrs, int64_t yrs, bool in_real) const;
     template <typename C>
-    int run_single_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, int64_t &done, cudaStream_t st) const;
+    int run_single_fast(Dev &d, int direction, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M,
+                        int64_t &done, cudaStream_t st) const;
     template <typename C>
     int run_fast(Dev &d, int direction, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, cudaStream_t st) const;
     bool v32_ok(size_t csize) const;

@@ -909,6 +909,13 @@ def test_single_kernel_fast_path(fm, orc, n):
         # every second column of a wider column-major batch: column stride 2 n
         wide = dev(np.repeat(x.astype(dt), 2, axis=1))
         assert np.abs(F.forward(wide[:, ::2]).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        # row-major operands (torch's default layout): the line-fastest variants of the same kernels
+        xr = torch.from_numpy(np.ascontiguousarray(x.astype(dt))).cuda()
+        assert xr.stride(1) == 1
+        assert np.abs(F.forward(xr).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        assert np.abs(F.backward(xr).cpu().numpy() - orc.fourier_backward(x)).max() / nx < tol
+        assert np.abs(C.forward(xr).cpu().numpy() - orc.circulant_forward(c, x)).max() / ncn < tol
+        assert np.abs(C.backward(xr).cpu().numpy() - orc.circulant_backward(c, x)).max() / ncn < tol
         # Toeplitz of order n/2 + 1 ... pads to n: rows beyond the order are masked on load and cropped on store
         nt = n // 2
         T = fm.Toeplitz(c[:nt].astype(dt), c[nt:2 * nt - 1].astype(dt))
@@ -916,6 +923,9 @@ def test_single_kernel_fast_path(fm, orc, n):
         ntn = np.linalg.norm(c) * np.linalg.norm(xt, axis=0).max() * np.log2(n)
         assert np.abs(T.forward(dev(xt.astype(dt))).cpu().numpy() - orc.toeplitz_forward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
         assert np.abs(T.backward(dev(xt.astype(dt))).cpu().numpy() - orc.toeplitz_backward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
+        xtr = torch.from_numpy(np.ascontiguousarray(xt.astype(dt))).cuda()
+        assert np.abs(T.forward(xtr).cpu().numpy() - orc.toeplitz_forward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
+        assert np.abs(T.backward(xtr).cpu().numpy() - orc.toeplitz_backward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
     # the two routes agree to rounding on the same input (same algorithm, different radix plan)
     import os
     import subprocess

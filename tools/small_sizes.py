@@ -1,6 +1,6 @@
 """Time the single-kernel sizes (L <= 8192) with CUDA events: Fourier / Circulant / Toeplitz forward, complex64, a column
 batch of 2^26 elements (512 MiB in, 512 MiB out: larger than L2), specialised route against the generic kernel
-(FMB_NO_FAST1=1).  Prints ms and the fraction of the measured HBM peak.
+(FMB_NO_FAST1=1).  Prints ms and the fraction of the measured HBM peak.  ROWMAJOR=1: batch-contiguous operands.
 
     python tools/small_sizes.py            # both routes, one subprocess each
 """
@@ -25,7 +25,10 @@ def worker():
     rng = np.random.default_rng(1)
     for n in (128, 256, 512, 1024, 2048, 4096, 8192):
         cols = (1 << 26) // n
-        x = torch.view_as_complex(torch.randn((cols, n, 2), dtype=torch.float32, device="cuda")).t()
+        if os.environ.get("ROWMAJOR", "0") == "1":
+            x = torch.view_as_complex(torch.randn((n, cols, 2), dtype=torch.float32, device="cuda"))
+        else:
+            x = torch.view_as_complex(torch.randn((cols, n, 2), dtype=torch.float32, device="cuda")).t()
         c = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
         nt = n // 2
         ops = [("fourier", fm.Fourier(n), x), ("circulant", fm.Circulant(c), x),
