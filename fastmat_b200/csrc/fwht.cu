@@ -320,6 +320,147 @@ template <typename T, int B, bool CONTIG, int LOGSTEP = -1> __global__ void __la
     fwht_tile<T, B, CONTIG, false, LOGSTEP>(p, (long long)blockIdx.x, reinterpret_cast<T *>(fwht_smem_raw), (int)threadIdx.x);
 }
 
+
+// ------------------------------------------------------------------------------------------- first pass, 4-byte types
+// Bits [0, 12) of a column-major column in TWO register sub-stages of six bits (64 values per thread, one exchange)
+// instead of three of four bits (two exchanges): a third less traffic through the load/store pipe, which - not HBM - is
+// what bounds the transform once the intermediate lives in L2 (profiles/r2_hadamard_o20_f32_ncu_full.txt: mio_throttle).
+//   * one CTA of 64 threads owns one line of 4096 contiguous elements (16 KB); each warp pulls its 8 KB half into shared
+//     memory with one bulk copy (cp.async.bulk, completion on an mbarrier): nothing passes through the load/store pipe or
+//     the registers on the way in, and the copy needs no coalescing from the thread layout;
+//   * sub-stage 1, bits [0, 6): thread u owns the 64 consecutive elements 64 u ... 64 u + 63, i.e. sixteen 16-byte chunks
+//     of its own 256-byte row.  All threads reading chunk s of their row at once would hit the same four banks, so lane k
+//     (= u mod 8) reads chunk s ^ k into register slot s (conflict free: the eight lanes of a quarter warp touch eight
+//     different chunks).  Slot s then holds a lane-dependent chunk, but slots s and s ^ d still hold partner chunks, and
+//     which of the two is the "low" one only decides where the sum and where the difference go:
+//         slot s <- v[s ^ d] + sigma v[s],  slot s ^ d <- v[s] - sigma v[s ^ d],   sigma = +1 / -1 by bit d of k
+//     - one fused multiply-add each, exact (multiplying by +-1 does not round), so every output is still produced by the
+//     reference's sequence of additions, bit for bit.  The row is written back in place the same skewed way;
+//   * sub-stage 2, bits [6, 12): thread u owns elements u + 64 j (lanes read consecutive words: conflict free), six plain
+//     levels, and 64 coalesced 128-byte stores per warp straight to global memory.
+template <typename T> struct HPm;          // b + sigma * a  for sigma = +-1
+template <> struct HPm<float> {
+    typedef float S;
+    static __device__ __forceinline__ float pm(float sigma, float a, float b) { return __fmaf_rn(sigma, a, b); }
+};
+template <> struct HPm<int32_t> {
+    typedef int32_t S;
+    static __device__ __forceinline__ int32_t pm(int32_t sigma, int32_t a, int32_t b) { return (int32_t)((uint32_t)sigma * (uint32_t)a + (uint32_t)b); }
+};
+
+__device__ __forceinline__ unsigned fwht_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <typename T> __global__ void __launch_bounds__(64, 10) fwht_first12_kernel(const __grid_constant__ FwhtFastPass p) {
+    static_assert(sizeof(T) == 4, "4-byte element types only");
+    typedef typename HPm<T>::S S;
+    extern __shared__ __align__(128) unsigned char fwht12_smem[];
+    T *const buf = reinterpret_cast<T *>(fwht12_smem);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long tile = blockIdx.x;
+    const long long col = tile >> p.log_tpc, tin = tile & (p.tiles_per_col - 1);
+    const T *gin = (const T *)p.in + col * p.in_cs + (tin << 12);
+    T *gout = (T *)p.out + col * p.out_cs + (tin << 12);
+    const unsigned bar = fwht_smem_u32(fwht12_smem + 16384) + 8u * (unsigned)w;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8192u) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(fwht_smem_u32(buf + 2048 * w)), "l"(gin + 2048 * w), "r"(8192u), "r"(bar) : "memory");
+    }
+    __syncwarp();
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "FWHT12_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra FWHT12_DONE_%=;\n\t"
+        "bra FWHT12_WAIT_%=;\n\t"
+        "FWHT12_DONE_%=:\n\t}" ::"r"(bar), "r"(0u), "r"(0x989680u) : "memory");
+    T v[64];
+    // ---- sub-stage 1: own row, skewed chunk order
+    const int k = lane & 7;
+    unsigned char *const row = reinterpret_cast<unsigned char *>(buf + 64 * tid);
+    const int kb = k << 4;
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        const int4 q = *reinterpret_cast<const int4 *>(row + ((s << 4) ^ kb));
+        v[4 * s + 0] = reinterpret_cast<const T &>(q.x); v[4 * s + 1] = reinterpret_cast<const T &>(q.y);
+        v[4 * s + 2] = reinterpret_cast<const T &>(q.z); v[4 * s + 3] = reinterpret_cast<const T &>(q.w);
+    }
+#pragma unroll
+    for (int lev = 0; lev < 2; ++lev) {                  // bits 0, 1: inside a chunk
+        const int d = 1 << lev;
+#pragma unroll
+        for (int r = 0; r < 64; ++r)
+            if ((r & d) == 0) { const T a = v[r], b = v[r | d]; v[r] = HOps<T>::add(a, b); v[r | d] = HOps<T>::sub(a, b); }
+    }
+#pragma unroll
+    for (int lev = 0; lev < 3; ++lev) {                  // bits 2, 3, 4: chunk bits 0 .. 2, lane-dependent orientation
+        const int d = 1 << lev;
+        const S sg = (k & d) ? (S)-1 : (S)1;
+#pragma unroll
+        for (int s = 0; s < 16; ++s)
+            if ((s & d) == 0) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const T a = v[4 * s + e], b = v[4 * (s | d) + e];
+                    v[4 * s + e] = HPm<T>::pm(sg, a, b);
+                    v[4 * (s | d) + e] = HPm<T>::pm(-sg, b, a);
+                }
+            }
+    }
+#pragma unroll
+    for (int r = 0; r < 32; ++r) {                       // bit 5: chunk bit 3 (not skewed)
+        const T a = v[r], b = v[r + 32];
+        v[r] = HOps<T>::add(a, b); v[r + 32] = HOps<T>::sub(a, b);
+    }
+#pragma unroll
+    for (int s = 0; s < 16; ++s) {
+        int4 q;
+        q.x = reinterpret_cast<const int &>(v[4 * s + 0]); q.y = reinterpret_cast<const int &>(v[4 * s + 1]);
+        q.z = reinterpret_cast<const int &>(v[4 * s + 2]); q.w = reinterpret_cast<const int &>(v[4 * s + 3]);
+        *reinterpret_cast<int4 *>(row + ((s << 4) ^ kb)) = q;
+    }
+    __syncthreads();
+    // ---- sub-stage 2: elements tid + 64 j
+#pragma unroll
+    for (int j = 0; j < 64; ++j) v[j] = buf[64 * j + tid];
+#pragma unroll
+    for (int lev = 0; lev < 6; ++lev) {
+        const int d = 1 << lev;
+#pragma unroll
+        for (int r = 0; r < 64; ++r)
+            if ((r & d) == 0) { const T a = v[r], b = v[r | d]; v[r] = HOps<T>::add(a, b); v[r | d] = HOps<T>::sub(a, b); }
+    }
+#pragma unroll
+    for (int j = 0; j < 64; ++j) gout[64 * j + tid] = v[j];
+}
+
+template <typename T> struct FwhtHas12 { static constexpr bool value = false; };
+template <> struct FwhtHas12<float> { static constexpr bool value = true; };
+template <> struct FwhtHas12<int32_t> { static constexpr bool value = true; };
+
+// launches the kernel above when it applies (4-byte type, 12-bit contiguous first pass, 16-byte aligned columns)
+template <typename T> static int fwht_first12_launch(const FwhtFastPass &p, long long lines, cudaStream_t st, bool &done) {
+    done = false;
+    if constexpr (FwhtHas12<T>::value) {
+        static const long off = getenv("FMB_FWHT_NO12") ? atol(getenv("FMB_FWHT_NO12")) : 0;
+        if (off || p.b != 12 || p.s != 0 || p.logT != 0) return FMB_OK;
+        if ((reinterpret_cast<unsigned long long>(p.in) & 15ull) || (p.in_cs & 3)) return FMB_OK;
+        if (lines > 2147483647LL) return FMB_OK;
+        const size_t smem = 16384 + 16;
+        static int attr_done = 0;
+        if (!attr_done) {
+            FMB_CUDA_OK(cudaFuncSetAttribute(fwht_first12_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = 1;
+        }
+        fwht_first12_kernel<T><<<(unsigned)lines, 64, smem, st>>>(p);
+        FMB_LAUNCH_OK();
+        done = true;
+    }
+    return FMB_OK;
+}
+
 template <typename T> static int fwht_fast_launch(const FwhtFastPass &p, unsigned grid, int threads, size_t smem, cudaStream_t st) {
     if (p.b == 8 && p.s == 12) {                        // second pass of order 20 (the BASELINE shape): compile-time stride
         static int attr_done = 0;
@@ -421,8 +562,10 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
             const long long grid = p.tiles_per_col * nc;
             if (grid > 2147483647LL || threads > 512 || threads < 1) { set_error("FWHT fast path: bad geometry"); return FMB_ERR_VALUE; }
             const size_t smem = (size_t)(1 << logT) * ((size_t)(1 << p.b) + ((size_t)(1 << p.b) >> 4) + 1) * sizeof(T);
-            int rc = fwht_fast_launch<T>(p, (unsigned)grid, threads, smem, st);
+            bool done12 = false;
+            int rc = fwht_first12_launch<T>(p, grid, st, done12);
             if (rc) return rc;
+            if (!done12 && (rc = fwht_fast_launch<T>(p, (unsigned)grid, threads, smem, st))) return rc;
             s += p.b;
         }
     }
