@@ -944,10 +944,20 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
     g.tiles = f.tiles; g.items_per_step = f.items_per_step;
     g.total_items = (unsigned)((f.nslabs + (int64_t)(f.npass - 1) * f.delay) * f.items_per_step);
     g.slot_stride = (long long)f.slab_cols * L;
+    g.ring_cs = L;
     g.y_slab_stride = (long long)f.slab_cols * ycs;
     g.L = L;
     g.done = (unsigned *)ws;
     g.ring = (C *)((char *)ws + f.counter_bytes);
+    // plain transforms in place: the intermediate is written into y and overwritten there by the second pass - no ring in
+    // the L2 working set and no dirty ring lines to write back (FMB_V32P_INPLACE=0: ring)
+    static const long inplace_env = env_long("FMB_V32P_INPLACE", 1);
+    const bool inplace = inplace_env && !two_ffts && (const void *)x != (const void *)y && (ycs & 1) == 0 &&
+                         (reinterpret_cast<uintptr_t>(y) & 15) == 0 && ycs >= L;
+    if (inplace) {
+        g.ring = (C *)y; g.ring_cs = ycs; g.slot_stride = (long long)f.slab_cols * ycs;
+        g.nslot = (int)f.nslabs + 1;                                 // slot = slab: nothing to wait for before pass A
+    }
     // L2 policies (createpolicy encodings): x is read once -> evict first; the ring is the working set -> evict last
     g.hint_x = hint_on ? 0x12F0000000000000ull : 0x1000000000000000ull;
     g.hint_ring = hint_on ? 0x14F0000000000000ull : 0x1000000000000000ull;
@@ -956,9 +966,10 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
     base.twL = (const C *)d.twL.p; base.twH = (const C *)d.twH.p; base.tw_shift = d.tw_shift;
     base.tw_mask = (unsigned)(((int64_t)1 << d.tw_shift) - 1);
     base.I = 1024; base.logI = 10;
-    {   // pass A: length R1 over n = f*R2 + i; ring[k1*R2 + i] * W^{i k1}
+    {   // pass A: length R1 over n = f*R2 + i; ring[k1*R2 + i] * W^{i k1}    (in place: y[i*R1 + k1])
         FastArgs<C> a = base;
         a.out_cs = L; a.out_ks = R2; a.out_is = 1;
+        if (inplace && kron_a == 0) { a.out_ks = 1; a.out_is = R1; }
         a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[0].p;
         g.pass[0] = a;
     }
@@ -976,7 +987,7 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
         a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
         a.tw = (const C *)d.twV[1].p;
         g.pass[1] = a;
-        variant = bwd ? VP_FC : VP_F;
+        variant = inplace ? (bwd ? VP_FIC : VP_FI) : (bwd ? VP_FC : VP_F);
     } else {
         FastArgs<C> a = base;                       // pass B': in place on the lines k1 of the ring
         a.out_cs = L; a.out_ks = 1; a.out_is = R2;
@@ -993,7 +1004,9 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
     CUtensorMap mx, mr;
     int rc;
     if ((rc = v32p_tensor_map(&mx, x, rows_in, xcs, M))) return rc;
-    if ((rc = v32p_tensor_map(&mr, g.ring, L, L, (int64_t)f.nslot * f.slab_cols))) return rc;
+    if (inplace) rc = v32p_tensor_map(&mr, y, L, ycs, M);
+    else rc = v32p_tensor_map(&mr, g.ring, L, L, (int64_t)f.nslot * f.slab_cols);
+    if (rc) return rc;
     rc = launch_v32p_f(variant, g, mx, mr, st);
     if (rc == FMB_ERR_NOTIMPL) rc = launch_v32p_c0(variant, g, mx, mr, st);
     if (rc == FMB_ERR_NOTIMPL) rc = launch_v32p_c1(variant, g, mx, mr, st);

@@ -49,6 +49,7 @@ struct V32PArgs {
     unsigned tiles;                // tiles per full slab and pass = slab_cols * 128
     unsigned items_per_step, total_items;
     long long slot_stride;         // elements between ring slots = slab_cols * L
+    long long ring_cs;             // elements between the columns of a slot (L; in-place variants: the ring IS y, slot = slab)
     long long y_slab_stride;       // elements between the outputs of consecutive slabs
     long long L;
     float2 *ring;
@@ -139,7 +140,7 @@ template <bool CONV> __device__ __forceinline__ bool v32p_ready(const V32PArgs &
 // Executed by ONE thread: request the tile of item `it` into `buf` (completion on `bar`).  Items that are not computed
 // (slabs outside the batch at both ends of the list, columns beyond a ragged last slab) still move 64 KB from a valid
 // address, which keeps the buffer / barrier protocol free of special cases.
-template <bool CONV>
+template <bool CONV, bool BOX1>
 __device__ __forceinline__ void v32p_request(const V32PArgs &g, const CUtensorMap *map_x, const CUtensorMap *map_ring, const V32PItem &it,
                                              unsigned buf, unsigned bar) {
     constexpr int LAST = CONV ? 2 : 1;
@@ -152,12 +153,12 @@ __device__ __forceinline__ void v32p_request(const V32PArgs &g, const CUtensorMa
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             v32p_tma_box(buf + q * 16384u, map_x, bar, (int)i0, 256 * q, slab * g.slab_cols + (int)col, g.hint_x);
-    } else if (CONV && it.p == LAST) {
+    } else if ((CONV && it.p == LAST) || (!CONV && BOX1)) {
 #pragma unroll
         for (int q = 0; q < 4; ++q)
             v32p_tma_box(buf + q * 16384u, map_ring, bar, (int)i0, 256 * q, slot * g.slab_cols + (int)col, g.hint_ring);
     } else {
-        const float2 *src = g.ring + (long long)slot * g.slot_stride + (long long)col * g.L + (long long)i0 * 1024;
+        const float2 *src = g.ring + (long long)slot * g.slot_stride + (long long)col * g.ring_cs + (long long)i0 * 1024;
 #pragma unroll
         for (int t = 0; t < V32_T; ++t)
             v32p_bulk_line(buf + (unsigned)(t * V32_RS * sizeof(float2)), src + t * 1024, 8192u, bar, g.hint_ring);
@@ -332,7 +333,7 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
                 __syncwarp();                         // lane 0 inherits what the other lanes acquired
             }
             if (lane == 0) {
-                v32p_request<CONV>(g, &map_x, &map_ring, it, base_s + j * (unsigned)V32P_BUF,
+                v32p_request<CONV, (OB & FO_LOAD_T) != 0>(g, &map_x, &map_ring, it, base_s + j * (unsigned)V32P_BUF,
                                    full_s + 8 * (2 * j + ((n / V32P_NBUF) & 1u)));
             }
             __syncwarp();
@@ -373,7 +374,7 @@ v32p_kernel(const __grid_constant__ V32PArgs g, const __grid_constant__ CUtensor
         if (it.compute) {
             const unsigned col = it.tile >> 7, i0 = (it.tile & 127u) << V32_LOGT;
             const int slot = it.slab % g.nslot;
-            C *const ring_col = g.ring + (long long)slot * g.slot_stride + (long long)col * g.L;
+            C *const ring_col = g.ring + (long long)slot * g.slot_stride + (long long)col * g.ring_cs;
             if (it.p == 0) v32p_tile<OA>(g.pass[0], buf, ring_col, i0, gt, group, handback);
             else if (it.p == LAST) {
                 C *const y_col = g.pass[LAST].out + (long long)it.slab * g.y_slab_stride + (long long)col * g.pass[LAST].out_cs;
@@ -437,7 +438,11 @@ template <unsigned OPT> int launch_v32t_variant(const FastArgs<float2> &a, const
 }
 
 // ---- variants (fft_engine.cu: run_v32p)
-enum V32PVariant { VP_F = 0, VP_FC = 1, VP_CV_N = 2, VP_CV_M = 3, VP_CVC_N = 4, VP_CVC_M = 5, VP_K = 6, VP_KC = 7 };
+enum V32PVariant { VP_F = 0, VP_FC = 1, VP_CV_N = 2, VP_CV_M = 3, VP_CVC_N = 4, VP_CVC_M = 5, VP_K = 6, VP_KC = 7, VP_FI = 8, VP_FIC = 9 };
+// in-place four-step (the intermediate lives in y itself, no ring): pass A writes its lines contiguously, y[i 1024 + k1];
+// pass B fetches strided boxes of y and overwrites exactly the addresses it read, y[k2 1024 + k1]
+constexpr unsigned V32P_FI_A = FO_LOAD_T | FO_TWIDDLE, V32P_FI_AC = V32P_FI_A | FO_IN_CONJ;
+constexpr unsigned V32P_FI_B = FO_LOAD_T | FO_STORE_T, V32P_FI_BC = V32P_FI_B | FO_OUT_CONJ;
 constexpr unsigned V32P_K_A = FO_LOAD_T | FO_STORE_T, V32P_K_AC = V32P_K_A | FO_IN_CONJ;     // Kron(Fourier, Fourier): no twiddle,
 constexpr unsigned V32P_K_B = 0u, V32P_K_BC = FO_OUT_CONJ;                                    // natural order, all rows kept
 

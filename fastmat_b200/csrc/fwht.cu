@@ -212,7 +212,22 @@ struct FwhtFastPass {
     int order;
     long long tiles_per_col;   // a power of two ...
     int log_tpc;               // ... and its log2: tile -> (column, tile in column) by shift and mask, no 64-bit division
+    unsigned long long pol_in, pol_out;   // L2 cache-hint policies of the loads / stores (4-byte types; 0: none)
 };
+
+// 4-byte accesses with an L2 eviction policy (createpolicy encodings: see fwht_fast)
+template <typename T> __device__ __forceinline__ T fwht_ld_hint(const T *p, unsigned long long pol) {
+    if constexpr (sizeof(T) == 4) {
+        unsigned r;
+        asm volatile("ld.global.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(r) : "l"(p), "l"(pol));
+        return reinterpret_cast<const T &>(r);
+    } else return *p;
+}
+template <typename T> __device__ __forceinline__ void fwht_st_hint(T *p, T v, unsigned long long pol) {
+    if constexpr (sizeof(T) == 4) {
+        asm volatile("st.global.L2::cache_hint.b32 [%0], %1, %2;" ::"l"(p), "r"(reinterpret_cast<const unsigned &>(v)), "l"(pol) : "memory");
+    } else *p = v;
+}
 
 template <typename T, int LEV0> __device__ __forceinline__ void fwht16(T (&v)[16]) {
 #pragma unroll
@@ -232,7 +247,7 @@ template <typename T, int LEV0> __device__ __forceinline__ void fwht16(T (&v)[16
 // sub-stages after the first one, resolved at compile time: the sub-stage starting at bit U covers bits [UU, UU+4) where
 // UU = min(U, B-4) (fewer than four bits left: re-use the top four positions and skip the levels already done)
 template <typename T, int B, int U>
-__device__ __forceinline__ void fwht_sub_chain(T (&v)[16], T *sl, T *gout_t, int q, long long step) {
+__device__ __forceinline__ void fwht_sub_chain(T (&v)[16], T *sl, T *gout_t, int q, long long step, unsigned long long pol_out) {
     constexpr int UU = (U + 4 > B) ? (B - 4) : U;
     constexpr int LEV0 = U - UU;
     const int l = q & ((1 << UU) - 1), h = q >> UU;
@@ -249,15 +264,20 @@ __device__ __forceinline__ void fwht_sub_chain(T (&v)[16], T *sl, T *gout_t, int
     fwht16<T, LEV0>(v);
     if constexpr (UU + 4 >= B) {                        // last sub-stage: straight to global memory
         T *dst = gout_t + (long long)m0 * step;
+        if (sizeof(T) == 4 && pol_out) {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) dst[(long long)(r << UU) * step] = v[r];
+            for (int r = 0; r < 16; ++r) fwht_st_hint(dst + (long long)(r << UU) * step, v[r], pol_out);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) dst[(long long)(r << UU) * step] = v[r];
+        }
     } else {
         __syncthreads();
         T *wb = sl + m0 + (m0 >> 4);
 #pragma unroll
         for (int r = 0; r < 16; ++r) wb[(r << UU) + ((r << UU) >> 4)] = v[r];
         __syncthreads();
-        fwht_sub_chain<T, B, U + 4>(v, sl, gout_t, q, step);
+        fwht_sub_chain<T, B, U + 4>(v, sl, gout_t, q, step, pol_out);
     }
 }
 
@@ -299,7 +319,13 @@ __device__ __forceinline__ void fwht_tile(const FwhtFastPass &p, long long tile,
         }
     } else {
 #pragma unroll
-        for (int r = 0; r < 16; ++r) v[r] = CG ? __ldcg(src + (long long)r * step) : src[(long long)r * step];
+        if (sizeof(T) == 4 && p.pol_in) {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = fwht_ld_hint(src + (long long)r * step, p.pol_in);
+        } else {
+#pragma unroll
+            for (int r = 0; r < 16; ++r) v[r] = CG ? __ldcg(src + (long long)r * step) : src[(long long)r * step];
+        }
     }
     fwht16<T, 0>(v);
     if constexpr (B == 4) {                             // a single sub-stage: back to global memory directly
@@ -311,7 +337,7 @@ __device__ __forceinline__ void fwht_tile(const FwhtFastPass &p, long long tile,
 #pragma unroll
         for (int r = 0; r < 16; ++r) wb[r] = v[r];
         __syncthreads();
-        fwht_sub_chain<T, B, 4>(v, sl, gout, q, step);
+        fwht_sub_chain<T, B, 4>(v, sl, gout, q, step, p.pol_out);
     }
 }
 
@@ -365,8 +391,12 @@ template <typename T> __global__ void __launch_bounds__(64, 10) fwht_first12_ker
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8192u) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(fwht_smem_u32(buf + 2048 * w)), "l"(gin + 2048 * w), "r"(8192u), "r"(bar) : "memory");
+        if (p.pol_in)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                         ::"r"(fwht_smem_u32(buf + 2048 * w)), "l"(gin + 2048 * w), "r"(8192u), "r"(bar), "l"(p.pol_in) : "memory");
+        else
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(fwht_smem_u32(buf + 2048 * w)), "l"(gin + 2048 * w), "r"(8192u), "r"(bar) : "memory");
     }
     __syncwarp();
     asm volatile(
@@ -432,8 +462,13 @@ template <typename T> __global__ void __launch_bounds__(64, 10) fwht_first12_ker
         for (int r = 0; r < 64; ++r)
             if ((r & d) == 0) { const T a = v[r], b = v[r | d]; v[r] = HOps<T>::add(a, b); v[r | d] = HOps<T>::sub(a, b); }
     }
+    if (p.pol_out) {
 #pragma unroll
-    for (int j = 0; j < 64; ++j) gout[64 * j + tid] = v[j];
+        for (int j = 0; j < 64; ++j) fwht_st_hint(gout + 64 * j + tid, v[j], p.pol_out);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 64; ++j) gout[64 * j + tid] = v[j];
+    }
 }
 
 template <typename T> struct FwhtHas12 { static constexpr bool value = false; };
@@ -455,6 +490,94 @@ template <typename T> static int fwht_first12_launch(const FwhtFastPass &p, long
             attr_done = 1;
         }
         fwht_first12_kernel<T><<<(unsigned)lines, 64, smem, st>>>(p);
+        FMB_LAUNCH_OK();
+        done = true;
+    }
+    return FMB_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------- strided 8-bit pass, 4-byte types
+// Bits [s, s + 8) of a column-major column, s >= 6: a tile is all 256 "mid" values x 64 consecutive low-index lines, and a
+// thread owns FOUR neighbouring lines, so every global and shared access is 128 bits wide: a quarter of the load/store
+// instructions of the one-line-per-thread kernel for the same bytes (the pass is bound by the load/store pipe, not by HBM,
+// once its input comes from L2).  Shared memory is laid out [mid][line]: the sixteen threads of a mid value cover its 256
+// bytes, conflict free without padding.  Two register sub-stages of four bits (ascending, as everywhere) and one exchange.
+template <typename T> struct alignas(16) FwhtVec4 { T x, y, z, w; };
+
+template <typename T> __device__ __forceinline__ void fwht16x4(FwhtVec4<T> (&v)[16]) {
+#pragma unroll
+    for (int lev = 0; lev < 4; ++lev) {
+        const int d = 1 << lev;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+            if ((r & d) == 0) {
+                const FwhtVec4<T> a = v[r], b = v[r | d];
+                v[r].x = HOps<T>::add(a.x, b.x); v[r].y = HOps<T>::add(a.y, b.y); v[r].z = HOps<T>::add(a.z, b.z); v[r].w = HOps<T>::add(a.w, b.w);
+                v[r | d].x = HOps<T>::sub(a.x, b.x); v[r | d].y = HOps<T>::sub(a.y, b.y); v[r | d].z = HOps<T>::sub(a.z, b.z); v[r | d].w = HOps<T>::sub(a.w, b.w);
+            }
+        }
+    }
+}
+
+template <typename T> __device__ __forceinline__ FwhtVec4<T> fwht_ld128(const FwhtVec4<T> *p) {
+    int4 q;
+    asm volatile("ld.global.L1::no_allocate.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p));
+    FwhtVec4<T> r;
+    r.x = reinterpret_cast<const T &>(q.x); r.y = reinterpret_cast<const T &>(q.y); r.z = reinterpret_cast<const T &>(q.z); r.w = reinterpret_cast<const T &>(q.w);
+    return r;
+}
+
+template <typename T, int LOGSTEP> __global__ void __launch_bounds__(256, 3) fwht_strided8_kernel(const __grid_constant__ FwhtFastPass p) {
+    static_assert(sizeof(T) == 4, "4-byte element types only");
+    typedef FwhtVec4<T> V;
+    extern __shared__ __align__(16) unsigned char fwht_s8_smem[];
+    V *const sm = reinterpret_cast<V *>(fwht_s8_smem);            // [256 mids][16 vectors]
+    const int tid = threadIdx.x, l16 = tid & 15, q = tid >> 4;
+    const int s = LOGSTEP >= 0 ? LOGSTEP : p.s;
+    const long long tile = blockIdx.x;
+    const long long col = tile >> p.log_tpc, tin = tile & (p.tiles_per_col - 1);
+    const int log_lo = s - 6;                                     // tiles along the low index: 2^s / 64
+    const long long hi = tin >> log_lo, lo0 = (tin & (((long long)1 << log_lo) - 1)) << 6;
+    const long long base = (hi << (s + 8)) + lo0 + 4 * l16;
+    const long long step = (long long)1 << s;
+    const T *gin = (const T *)p.in + col * p.in_cs + base;
+    T *gout = (T *)p.out + col * p.out_cs + base;
+    V v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = fwht_ld128(reinterpret_cast<const V *>(gin + (long long)(16 * q + r) * step));
+    fwht16x4<T>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[(16 * q + r) * 16 + l16] = v[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = sm[(q + 16 * r) * 16 + l16];
+    fwht16x4<T>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) *reinterpret_cast<V *>(gout + (long long)(q + 16 * r) * step) = v[r];
+}
+
+template <typename T> static int fwht_strided8_launch(const FwhtFastPass &p, long long ncols, cudaStream_t st, bool &done) {
+    done = false;
+    if constexpr (FwhtHas12<T>::value) {
+        static const long off = getenv("FMB_FWHT_NO_S8") ? atol(getenv("FMB_FWHT_NO_S8")) : 0;
+        if (off || p.b != 8 || p.s < 6 || p.order - p.s < 8) return FMB_OK;
+        if ((reinterpret_cast<unsigned long long>(p.in) & 15ull) || (reinterpret_cast<unsigned long long>(p.out) & 15ull) ||
+            (p.in_cs & 3) || (p.out_cs & 3)) return FMB_OK;
+        FwhtFastPass q = p;
+        q.log_tpc = p.order - 8 - 6;                              // tiles per column: 2^(order - 8) lines / 64
+        q.tiles_per_col = (long long)1 << q.log_tpc;
+        const long long grid = q.tiles_per_col * ncols;
+        if (grid > 2147483647LL) return FMB_OK;
+        const size_t smem = 256 * 64 * sizeof(T);
+        static int attr_done = 0;
+        if (!attr_done) {
+            FMB_CUDA_OK(cudaFuncSetAttribute(fwht_strided8_kernel<T, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FMB_CUDA_OK(cudaFuncSetAttribute(fwht_strided8_kernel<T, -1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_done = 1;
+        }
+        if (p.s == 12) fwht_strided8_kernel<T, 12><<<(unsigned)grid, 256, smem, st>>>(q);
+        else fwht_strided8_kernel<T, -1><<<(unsigned)grid, 256, smem, st>>>(q);
         FMB_LAUNCH_OK();
         done = true;
     }
@@ -550,6 +673,20 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
             p.out = (char *)y + (size_t)(c0 * ycs) * sizeof(T);
             p.out_cs = ycs;
             p.b = bits[pi]; p.s = s; p.order = order;
+            // L2 eviction policies of the multi-pass pipeline (FMB_FWHT_HINT, bit mask): 1 = the column input is read
+            // evict-first, 2 = intermediates are written evict-last, 4 = intermediates are read evict-first (they are
+            // overwritten in place), 8 = the final result is written evict-first
+            {
+                static const long hint = getenv("FMB_FWHT_HINT") ? atol(getenv("FMB_FWHT_HINT")) : 0;
+                const unsigned long long EV_FIRST = 0x12F0000000000000ull, EV_LAST = 0x14F0000000000000ull;
+                const bool last = (pi + 1 == bits.size());
+                if (bits.size() > 1) {
+                    if (first && (hint & 1)) p.pol_in = EV_FIRST;
+                    if (!first && (hint & 4)) p.pol_in = EV_FIRST;
+                    if (!last && (hint & 2)) p.pol_out = EV_LAST;
+                    if (last && (hint & 8)) p.pol_out = EV_FIRST;
+                }
+            }
             int logT = 0;
             if (s > 0) {
                 int want = tile_elems >> p.b;                      // lines per tile
@@ -565,6 +702,7 @@ static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs
             bool done12 = false;
             int rc = fwht_first12_launch<T>(p, grid, st, done12);
             if (rc) return rc;
+            if (!done12 && (rc = fwht_strided8_launch<T>(p, nc, st, done12))) return rc;
             if (!done12 && (rc = fwht_fast_launch<T>(p, (unsigned)grid, threads, smem, st))) return rc;
             s += p.b;
         }

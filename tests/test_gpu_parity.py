@@ -958,3 +958,46 @@ def test_kron_fourier_pass_length_64(fm, orc, dims):
         xd = dev(x.astype(dt))
         assert np.abs(K.forward(xd).cpu().numpy() - orc.kron_fourier_forward(dims, x)).max() / nx < tol
         assert np.abs(K.backward(xd).cpu().numpy() - orc.kron_fourier_backward(dims, x)).max() / nx < tol
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("order", [24, 28])
+def test_hadamard_large_orders_exact(fm, order):
+    """Orders above 20 chain the 12-bit first pass (64 values per thread) with strided passes: 12 + 6 + 6 for order 24,
+    12 + 8 + 8 for order 28 (the 128-bit strided kernel with a compile-time and with a run-time stride).  int32 ring
+    arithmetic makes everything exact: H(H x) = 2^order x, and single outputs against the defining signed sum."""
+    n = 2 ** order
+    H = fm.Hadamard(order)
+    g = torch.Generator(device='cuda').manual_seed(order)
+    x = torch.randint(-2 ** 31, 2 ** 31 - 1, (1, n), dtype=torch.int32, device='cuda', generator=g).t()
+    y = H.forward(x)
+    idx = torch.arange(n, device='cuda', dtype=torch.int64)
+    for k in (0, 1, n - 1, 0x5A5A5A5 % n, 3 * 4096 + 17, (1 << (order - 1)) + 4096 * 255 + 77):
+        v = idx & k                                       # parity of popcount(n & k) by xor folding
+        for sh in (32, 16, 8, 4, 2, 1):
+            v = v ^ (v >> sh)
+        sign = 1 - 2 * (v & 1)
+        want = int((x[:, 0].to(torch.int64) * sign).sum().item())
+        want = (want + 2 ** 31) % 2 ** 32 - 2 ** 31       # wrap to int32
+        assert int(y[k, 0].item()) == want, k
+    z = H.forward(y)
+    assert torch.equal(z, x * (2 ** order))
+
+
+@pytest.mark.gpu
+def test_hadamard_unaligned_columns_bit_identical(fm):
+    """The bulk-copy / 128-bit kernels need 16-byte aligned columns; a batch whose column stride is odd takes the scalar
+    kernels and must give the same bits (order 20, float32 and int32)."""
+    order, m = 20, 5
+    n = 2 ** order
+    H = fm.Hadamard(order)
+    g = torch.Generator(device='cuda').manual_seed(11)
+    for dt in (torch.float32, torch.int32):
+        if dt == torch.float32:
+            base = torch.randn((m, n + 1), dtype=dt, device='cuda', generator=g)
+        else:
+            base = torch.randint(-2 ** 31, 2 ** 31 - 1, (m, n + 1), dtype=dt, device='cuda', generator=g)
+        xu = base[:, 1:].t()                              # column stride n + 1, first element 4 bytes off alignment
+        assert xu.stride(0) == 1 and xu.stride(1) == n + 1
+        xa = xu.t().contiguous().t()
+        assert torch.equal(H.forward(xu), H.forward(xa))

@@ -17,6 +17,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <chrono>
+#include <functional>
 #include <string>
 #include <vector>
 
@@ -150,12 +152,26 @@ int main(int argc, char **argv) {
     run();
     const int64_t launches = a.launches() - l0;
     CK(cudaStreamSynchronize(st));
+    std::function<void()> direct = run;
+    cudaGraphExec_t gexec = nullptr;
+    if (getenv("CBENCH_GRAPH") && atoi(getenv("CBENCH_GRAPH"))) {                       // experiment: the whole apply as one CUDA graph launch
+        cudaGraph_t graph;
+        CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        direct();
+        CK(cudaStreamEndCapture(st, &graph));
+        CK(cudaGraphInstantiate(&gexec, graph, 0));
+        CK(cudaGraphLaunch(gexec, st));
+        CK(cudaStreamSynchronize(st));
+    }
+    auto run2 = [&]() { if (gexec) CK(cudaGraphLaunch(gexec, st)); else direct(); };
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
-    double best = 1e30, sum = 0;
+    double best = 1e30, sum = 0, enq = 0;
     for (int r = 0; r < reps; ++r) {
         CK(cudaEventRecord(e0, st));
-        run();
+        const auto h0 = std::chrono::steady_clock::now();
+        run2();
+        enq += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
         CK(cudaEventRecord(e1, st));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -165,7 +181,7 @@ int main(int argc, char **argv) {
     if (seconds > 0) {
         const int n = std::max(1, (int)(seconds * 1e3 / (sum / reps)) + 1);
         CK(cudaEventRecord(e0, st));
-        for (int r = 0; r < n; ++r) run();
+        for (int r = 0; r < n; ++r) run2();
         CK(cudaEventRecord(e1, st));
         CK(cudaEventSynchronize(e1));
         float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
@@ -174,7 +190,7 @@ int main(int argc, char **argv) {
     if (getenv("CBENCH_PROFILE")) {                    // one apply inside a profiler range (ncu --replay-mode range: concurrent kernels as they run)
         CK(cudaStreamSynchronize(st));
         CK(cudaProfilerStart());
-        run();
+        run2();
         CK(cudaStreamSynchronize(st));
         CK(cudaProfilerStop());
     }
@@ -187,6 +203,7 @@ int main(int argc, char **argv) {
     const double gb = alg_bytes_per_col * cols / 1e9, mean = sum / reps;
     printf("%-8s cols %5ld  best %8.3f ms  mean %8.3f ms  %7.0f GB/s  frac %.3f", op.c_str(), cols, best, mean, gb / mean * 1e3, gb / mean * 1e3 / peak);
     if (seconds > 0) printf("  sustained %8.3f ms frac %.3f", sustained, gb / sustained * 1e3 / peak);
+    printf("  enqueue %.3f ms", enq / reps);      // host time inside the apply call (no synchronisation): launch-bound if close to the device time
     printf("  launches %lld  chk %.9e %.9e\n", (long long)launches, hcs[0], hcs[1]);
     if (void (*dump)() = (void (*)())dlsym(a.h, "fmb_debug_dump")) dump();      // instrumented experiment builds only
     a.destroy(plan);
