@@ -705,6 +705,13 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
         tma_a = (v32t == 1 || (v32t == 2 && rows_in == L)) && v32p_tensor_map(&map_x, x, rows_in, xcs, M) == FMB_OK;
         tma_c = two_ffts && (v32t == 1 || v32t == 3) && v32p_tensor_map(&map_ring, ws, L, L, (int64_t)std::max(ns, 1) * slab) == FMB_OK;
     }
+    // Convolutions that keep all L rows (Circulant) run IN PLACE on y: pass A writes y, the middle pass transforms its
+    // lines there and the last pass reads and writes the same addresses (same strided geometry on both sides).  No ring in
+    // the L2 working set, and no dirty ring lines for the L2 to write back to DRAM (FMB_V32_INPLACE=0: ring).
+    static const long inplace_env = env_long("FMB_V32_INPLACE", 1);
+    const bool inplace = inplace_env && two_ffts && kron_a == 0 && rows_out == L && (const void *)x != (const void *)y && ycs >= L;
+    const int64_t wcs = inplace ? ycs : L;                        // column stride of the intermediate
+    if (inplace) tma_c = false;
     PipeScope pipe;
     if ((rc = pipe.begin(ns, st))) return rc;
     // FMB_L2_PERSIST=1 (experiments): the ring of intermediates is the only data with reuse - ask the L2 to keep it
@@ -741,6 +748,7 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
             ws = (char *)ws_base + (size_t)(slab_idx % ns) * (size_t)slab * (size_t)L * sizeof(C);
             ring_col0 = (int)((slab_idx % ns) * slab);
         }
+        if (inplace) ws = (C *)y + c0 * ycs;
         const unsigned tiles = (unsigned)(nc * 1024);          // lines; the launcher divides by its tile width
         FastArgs<C> base;
         memset(&base, 0, sizeof(base));
@@ -766,7 +774,7 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
         {   // ---- pass A: length R1 over n = f*R2 + i (lines i contiguous); out ws[k1*R2 + i], times W^{i k1}
             FastArgs<C> a = base;
             a.in = (const C *)x + c0 * xcs; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
-            a.out = (C *)ws; a.out_cs = L; a.out_ks = R2; a.out_is = 1;
+            a.out = (C *)ws; a.out_cs = wcs; a.out_ks = R2; a.out_is = 1;
             a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
             a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[0].p;
             a.pre = pre_d;
@@ -798,15 +806,15 @@ int ConvEngine::run_v32(Dev &d, int direction, const void *x, int64_t xcs, void 
         } else {
             {   // ---- pass B': in place on ws lines k1: FFT over n2, * spectrum[k1][k2], conj, FFT, * W^{k1 m2}
                 FastArgs<C> a = base;
-                a.in = (const C *)ws; a.in_cs = L; a.in_fs = 1; a.in_is = R2;
-                a.out = (C *)ws; a.out_cs = L; a.out_ks = 1; a.out_is = R2;
+                a.in = (const C *)ws; a.in_cs = wcs; a.in_fs = 1; a.in_is = R2;
+                a.out = (C *)ws; a.out_cs = wcs; a.out_ks = 1; a.out_is = R2;
                 a.mid = (const C *)d.mid.p; a.mid_is = R2;
                 a.tw = (const C *)d.twV[1].p; a.twS = (const C *)d.twS32[1].p;
                 if ((rc = launch_v32(tw_in_c ? (bwd ? V32_BMC_N : V32_BM_N) : (bwd ? V32_BMC : V32_BM), a, tiles, st))) return rc;
             }
             {   // ---- pass C: length R1 over k1 (stride R2 in ws), lines m2; conj, post-multiply, truncate; out y[m1*R2 + m2]
                 FastArgs<C> a = base;
-                a.in = (const C *)ws; a.in_cs = L; a.in_fs = R2; a.in_is = 1;
+                a.in = (const C *)ws; a.in_cs = wcs; a.in_fs = R2; a.in_is = 1;
                 a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R2; a.out_is = 1;
                 a.out_n = (int)rows_out; a.out_lk = R2; a.out_li = 1;
                 a.post = post_d;
