@@ -510,15 +510,29 @@ def run_ours(args):
         except Exception as e:
             extras['lfsr_circulant_forward_o20_f32'] = {'error': repr(e)}
         del xf
-        # mid sizes: 2^14 / 2^15 (pass length 128) run the specialised passes since round 2; 2^13 (one shared-memory kernel)
-        # and the 2^a 3^b paddings fastmat's planner emits (6144, 110592) still run the generic
-        # run-time-radix kernels: measured, not yet specialised
-        for nn, mm, tag in ((1 << 13, 1024, 'generic_kernel'), (1 << 14, 1024, 'fast_path'), (1 << 15, 1024, 'fast_path'),
+        # mid sizes: 2^13 ... 2^15 (pass lengths 64 / 128) run the specialised passes since round 2; the 2^a 3^b paddings
+        # fastmat's planner emits (6144, 110592) still run the generic run-time-radix kernels
+        for nn, mm, tag in ((1 << 13, 1024, 'fast_path'), (1 << 14, 1024, 'fast_path'), (1 << 15, 1024, 'fast_path'),
                             (6144, 1024, 'generic_kernel'), (110592, 256, 'generic_kernels')):
             Fs = fm.Fourier(nn)
             xs_ = crandn(nn, mm)
             rec('fourier_forward_%d_c64_%s' % (nn, tag), lambda: Fs.forward(xs_), mm, 16.0 * nn, k=10, sustain=0)
             del xs_, Fs
+        # lengths that fit on chip: ONE kernel per apply (FFT -> spectrum -> FFT in shared memory for Circulant / Toeplitz,
+        # zero padding folded into the loads); batch of 2^26 elements so that the operands exceed L2
+        for nn in (1 << 10, 1 << 12):
+            mm = (1 << 26) // nn
+            xs_ = crandn(nn, mm)
+            cs_ = (rng.standard_normal(nn) + 1j * rng.standard_normal(nn)).astype(np.complex64)
+            Fs, Cs = fm.Fourier(nn), fm.Circulant(cs_)
+            Ts = fm.Toeplitz(cs_[:nn // 2], cs_[nn // 2:nn - 1])
+            rec('fourier_forward_%d_c64_single_kernel' % nn, lambda: Fs.forward(xs_), mm, 16.0 * nn, k=10, sustain=0)
+            rec('circulant_forward_%d_c64_single_kernel' % nn, lambda: Cs.forward(xs_), mm, 16.0 * nn, k=10, sustain=0)
+            xt_ = xs_[:nn // 2, :]
+            rec('toeplitz_forward_%d_c64_single_kernel' % (nn // 2), lambda: Ts.forward(xt_), mm, 8.0 * nn, k=10, sustain=0)
+            xr_ = xs_.contiguous()
+            rec('fourier_forward_%d_c64_single_kernel_row_major' % nn, lambda: Fs.forward(xr_), mm, 16.0 * nn, k=10, sustain=0)
+            del xs_, xt_, xr_, Fs, Cs, Ts
         x16 = crandn(1 << 16, 64).to(torch.complex128)
         F16 = fm.Fourier(1 << 16)
         rec('fourier_forward_2^16_c128_64cols', lambda: F16.forward(x16), 64, 32.0 * (1 << 16), k=20)

@@ -558,6 +558,11 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
     int rc;
     // pipelined slabs: fork the caller's stream into ns internal streams, slab k runs on stream k % ns over ring slot
     // k % ns of the workspace, and the caller's stream joins them all at the end (stream-ordered for the caller)
+    // plain transforms keep their intermediate in y itself: the second pass reads and writes the same addresses (same
+    // geometry on both sides), so there is no ring in the L2 working set (FMB_FAST_INPLACE=0: ring in the workspace)
+    static const long inplace_env = env_long("FMB_FAST_INPLACE", 1);
+    const bool inplace = inplace_env && !two_ffts && rows_out == L && rows_in == L && (const void *)x != (const void *)y && ycs >= L;
+    const int64_t wcs = inplace ? ycs : L;
     PipeScope pipe;
     if ((rc = pipe.begin(ns, st))) return rc;
     void *const ws_base = ws;
@@ -568,6 +573,7 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
             st = pipe.stream(slab_idx);
             ws = (char *)ws_base + (size_t)(slab_idx % ns) * (size_t)slab * (size_t)L * sizeof(C);
         }
+        if (inplace) ws = (C *)y + c0 * ycs;
         FastArgs<C> base;
         memset(&base, 0, sizeof(base));
         base.ncols = (int)nc;
@@ -577,13 +583,13 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
             // Kron(Fourier(R1), Fourier(R2)): 2-D transform of the row-major (R1, R2) image, no twiddle between the passes
             FastArgs<C> a = base;                                     // over i1 (stride R2), lines i2; natural order out
             a.in = (const C *)x + c0 * xcs; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
-            a.out = (C *)ws; a.out_cs = L; a.out_ks = R2; a.out_is = 1;
+            a.out = (C *)ws; a.out_cs = wcs; a.out_ks = R2; a.out_is = 1;
             a.I = R2; a.logI = l2;
             a.out_n = (int)L; a.out_lk = R2; a.out_li = 1;
             a.tw = (const C *)d.twF[0].p;
             if ((rc = fast_launch(l1, bwd ? FV_K_AC_ : FV_B_F_, a, (unsigned)((nc * R2) >> t1), st))) return rc;
             FastArgs<C> b2 = base;                                    // over i2 (contiguous), lines k1
-            b2.in = (const C *)ws; b2.in_cs = L; b2.in_fs = 1; b2.in_is = R2;
+            b2.in = (const C *)ws; b2.in_cs = wcs; b2.in_fs = 1; b2.in_is = R2;
             b2.out = (C *)y + c0 * ycs; b2.out_cs = ycs; b2.out_ks = 1; b2.out_is = R2;
             b2.I = R1; b2.logI = l1;
             b2.out_n = (int)L; b2.out_lk = 1; b2.out_li = R2;
@@ -595,7 +601,7 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
         {
             FastArgs<C> a = base;
             a.in = (const C *)x + c0 * xcs; a.in_cs = xcs; a.in_fs = R2; a.in_is = 1;
-            a.out = (C *)ws; a.out_cs = L; a.out_ks = 1; a.out_is = R1;
+            a.out = (C *)ws; a.out_cs = wcs; a.out_ks = 1; a.out_is = R1;
             a.I = R2; a.logI = l2;
             a.in_n = (int)rows_in; a.in_lf = R2; a.in_li = 1;
             a.tw = (const C *)d.twF[0].p; a.twS = (const C *)d.twS[0].p;
@@ -609,7 +615,7 @@ int ConvEngine::run_fast(Dev &d, int direction, const void *x, int64_t xcs, void
         if (!two_ffts) {
             // ---- pass B: length R2 over f = n2 (stride R1 in ws), lines i = k1 < R1; out y[k*R1 + i]
             FastArgs<C> a = base;
-            a.in = (const C *)ws; a.in_cs = L; a.in_fs = R1; a.in_is = 1;
+            a.in = (const C *)ws; a.in_cs = wcs; a.in_fs = R1; a.in_is = 1;
             a.out = (C *)y + c0 * ycs; a.out_cs = ycs; a.out_ks = R1; a.out_is = 1;
             a.I = R1; a.logI = l1;
             a.out_n = (int)rows_out; a.out_lk = R1; a.out_li = 1;
