@@ -225,7 +225,7 @@ def run_reference_arm(args):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -592,10 +592,19 @@ def run_ours(args):
             'config5_solvers': config5,
             'extras': extras,
         }
-        print(json.dumps(line))
+        emit(line)
     if distributed:
         dist.destroy_process_group()
     return 0
+
+
+_JSON_OUT = None
+
+
+def emit(line):
+    out = _JSON_OUT or sys.stdout
+    out.write(json.dumps(line) + '\n')
+    out.flush()
 
 
 def main():
@@ -614,6 +623,12 @@ def main():
     ap.add_argument('--no-e2e', action='store_true', dest='no_e2e')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
     args = ap.parse_args()
+    # stdout carries the ONE JSON line and nothing else: whatever libraries write to file descriptor 1 (NCCL's version
+    # banner, for one) goes to stderr; the line itself is written to a private duplicate of the original stdout
+    global _JSON_OUT
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), 'w')
+    os.dup2(2, 1)
     if args.impl == 'reference':
         return run_reference_arm(args)
     return run_ours(args)

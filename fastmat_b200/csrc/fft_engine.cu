@@ -196,7 +196,7 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
                 for (int kk = 0; kk < 256; ++kk) { w.push_back(root((int64_t)kk * 2 * p2, Rg)); w.push_back(root((int64_t)kk * (2 * p2 + 1), Rg)); }
             int rc = upload_cvec<C>(d.twF[g], w);
             if (rc) return rc;
-            if (Rg == 1024 && shape.npass == 2) {
+            if (Rg == 1024 && (shape.npass == 2 || two_ffts)) {
                 // 32-values-per-thread passes (fft_v32.cuh): second-stage twiddles {W_1024^{kk 2p}, W_1024^{kk (2p+1)}} at
                 // [p * 32 + kk], stored twice (see v32_pass_kernel), and the four-step step factor W_L^{32 i}
                 w.clear();
@@ -204,7 +204,7 @@ template <typename C> int ConvEngine::ensure_dev(Dev &d) const {
                     for (int p2 = 0; p2 < 16; ++p2)
                         for (int kk = 0; kk < 32; ++kk) { w.push_back(root(kk * 2 * p2, 1024)); w.push_back(root(kk * (2 * p2 + 1), 1024)); }
                 if ((rc = upload_cvec<C>(d.twV[g], w))) return rc;
-                if (kron_a == 0) {
+                if (kron_a == 0 && shape.npass == 2) {
                     unit_roots(L, L / Rg, 32, w);
                     if ((rc = upload_cvec<C>(d.twS32[g], w))) return rc;
                 }
@@ -497,6 +497,7 @@ template <typename C> bool ConvEngine::fast_ok(int64_t xrs, int64_t yrs, bool in
 // load mask and its cropping the store mask.  Row-major operands (batch contiguous) use the line-fastest thread order:
 // the T columns of a tile are the contiguous direction (8 T bytes per row: full 32-byte sectors from T = 4, i.e. up to
 // L = 2048).  Handles the first M - M % T columns; returns how many in `done`.
+static int launch_v32(unsigned opt, const FastArgs<float2> &a, unsigned lines, cudaStream_t st);
 template <typename C>
 int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs,
                                 int64_t ycs, int64_t M, int64_t &done, cudaStream_t st) const {
@@ -504,10 +505,30 @@ int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xr
 #ifdef FMB_EMULATE
     return FMB_OK;
 #else
-    static const long off = env_long("FMB_NO_FAST", 0), off1 = env_long("FMB_NO_FAST1", 0);
+    static const long off = env_long("FMB_NO_FAST", 0), off1 = env_long("FMB_NO_FAST1", 0), no_v32 = env_long("FMB_NO_V32", 0);
     const int l = ilog2_host(L);
     if (off || off1 || !shape.pow2 || shape.npass != 1 || !fast_has((const C *)nullptr, l)) return FMB_OK;
     if (!pre.empty() || !post.empty() || (two_ffts && mid.empty())) return FMB_OK;
+    if constexpr (sizeof(C) == sizeof(float2)) {
+        // Circulant of length 1024 on a contiguous column-major batch: the middle pass of the 2^20 transforms IS this
+        // operator (FFT -> spectrum -> FFT on contiguous, warp-private lines, 32 values per thread, fused twiddle
+        // butterflies) with the same spectrum for every line - 1.8x the 16-value kernel's rate
+        if (L == 1024 && two_ffts && n_in == L && n_out == L && !no_v32 && xrs == 1 && yrs == 1 && xcs == 1024 && ycs == 1024 &&
+            (M & ~(int64_t)7) > 0 && M < ((int64_t)1 << 31)) {
+            const int64_t Mf = M & ~(int64_t)7;
+            FastArgs<float2> a;
+            memset(&a, 0, sizeof(a));
+            a.ncols = (int)((Mf + 1023) / 1024);
+            a.in = (const float2 *)x; a.in_cs = 1024 * 1024; a.in_fs = 1; a.in_is = 1024;
+            a.out = (float2 *)y; a.out_cs = 1024 * 1024; a.out_ks = 1; a.out_is = 1024;
+            a.I = 1024; a.logI = 10;
+            a.mid = (const float2 *)d.mid.p; a.mid_is = 0;
+            a.tw = (const float2 *)d.twV[0].p;
+            int rc = launch_v32(direction == FMB_BACKWARD ? V32_1MC : V32_1M, a, (unsigned)Mf, st);
+            if (rc == FMB_OK) done = Mf;
+            return rc;
+        }
+    }
     const int lt = fast_logt((const C *)nullptr, l);
     const int64_t T = (int64_t)1 << lt, Mf = M & ~(T - 1);
     const bool rm = !(xrs == 1 && yrs == 1);

@@ -533,6 +533,8 @@ constexpr unsigned V32_K_A = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK;              
 constexpr unsigned V32_K_AC = V32_K_A | FO_IN_CONJ;
 constexpr unsigned V32_K_B = FO_OUT_MASK;                                        // Kron: over i2 (contiguous)
 constexpr unsigned V32_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
+constexpr unsigned V32_1M = FO_TWO_FFTS | FO_OUT_CONJ;                           // whole Circulant of length 1024 on contiguous columns
+constexpr unsigned V32_1MC = V32_1M | FO_MID_CONJ;                               // (fft_engine.cu: run_single_fast)
 
 // `shape` selects the tile / occupancy instantiation: strided passes 0 = 8 lines, 2 CTAs per SM (128 registers), 1 = 8 lines,
 // 3 CTAs per SM (80 registers); the middle pass of a convolution (warp-private lines, no CTA barrier) additionally
