@@ -18,7 +18,7 @@ fi
 OUT=${OUT:-fastmat_b200/lib/libfastmat_b200.so}
 OBJDIR=build/obj$(echo "${EXTRA_DEFS:-}" | tr -c 'A-Za-z0-9_\n' '_')
 mkdir -p "$(dirname "$OUT")" "$OBJDIR"
-UNITS="capi fft_engine fft_k_f32_pow2 fft_k_f32_gen fft_k_f64_pow2 fft_k_f64_gen fft_fast_f32_L6 fft_fast_f64_L6 fft_fast_f32_L7 fft_fast_f64_L7 fft_fast_f32_L8 fft_fast_f32_L9 fft_fast_f32_L10 fft_fast_f32_L11 fft_fast_f32_L12 fft_v32_a fft_v32_b fft_v32_m fft_v32_c fft_v32p_f fft_v32p_c0 fft_v32p_c1 fft_v32t fft_fast_f64_L8 fft_fast_f64_L9 fft_fast_f64_L10 fft_fast_f64_L11 fwht elementwise"
+UNITS="capi fft_engine fft_k_f32_pow2 fft_k_f32_gen fft_k_f64_pow2 fft_k_f64_gen fft_fast_f32_L6 fft_fast_f64_L6 fft_fast_f32_L7 fft_fast_f64_L7 fft_fast_f32_L8 fft_fast_f32_L9 fft_fast_f32_L10 fft_fast_f32_L11 fft_fast_f32_L12 fft_v32_a fft_v32_b fft_v32_m fft_v32_c fft_v32_1 fft_v32p_f fft_v32p_c0 fft_v32p_c1 fft_v32t fft_fast_f64_L8 fft_fast_f64_L9 fft_fast_f64_L10 fft_fast_f64_L11 fwht elementwise"
 OBJS=""
 for f in $UNITS; do OBJS="$OBJS $OBJDIR/$f.o"; done
 cat > "$OBJDIR/Makefile" <<EOF

@@ -510,21 +510,29 @@ int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xr
     if (off || off1 || !shape.pow2 || shape.npass != 1 || !fast_has((const C *)nullptr, l)) return FMB_OK;
     if (!pre.empty() || !post.empty() || (two_ffts && mid.empty())) return FMB_OK;
     if constexpr (sizeof(C) == sizeof(float2)) {
-        // Circulant of length 1024 on a contiguous column-major batch: the middle pass of the 2^20 transforms IS this
-        // operator (FFT -> spectrum -> FFT on contiguous, warp-private lines, 32 values per thread, fused twiddle
-        // butterflies) with the same spectrum for every line - 1.8x the 16-value kernel's rate
-        if (L == 1024 && two_ffts && n_in == L && n_out == L && !no_v32 && xrs == 1 && yrs == 1 && xcs == 1024 && ycs == 1024 &&
+        // Convolutions of FFT length 1024 (Circulant(1024); Toeplitz padded to 1024) on column-major batches: the middle
+        // pass of the 2^20 transforms IS this operator (FFT -> spectrum -> FFT on contiguous, warp-private lines, 32 values
+        // per thread, fused twiddle butterflies) with the same spectrum for every line and the column stride as line stride
+        // - 1.8x the 16-value kernel's rate.  Zero padding to exactly twice the length is pruned (never loaded / stored).
+        const int64_t rin = direction == FMB_BACKWARD ? n_out : n_in, rout = direction == FMB_BACKWARD ? n_in : n_out;
+        if (L == 1024 && two_ffts && !no_v32 && xrs == 1 && yrs == 1 && xcs < ((int64_t)1 << 20) && ycs < ((int64_t)1 << 20) &&
             (M & ~(int64_t)7) > 0 && M < ((int64_t)1 << 31)) {
             const int64_t Mf = M & ~(int64_t)7;
             FastArgs<float2> a;
             memset(&a, 0, sizeof(a));
             a.ncols = (int)((Mf + 1023) / 1024);
-            a.in = (const float2 *)x; a.in_cs = 1024 * 1024; a.in_fs = 1; a.in_is = 1024;
-            a.out = (float2 *)y; a.out_cs = 1024 * 1024; a.out_ks = 1; a.out_is = 1024;
+            a.in = (const float2 *)x; a.in_cs = 1024 * xcs; a.in_fs = 1; a.in_is = (int)xcs;
+            a.out = (float2 *)y; a.out_cs = 1024 * ycs; a.out_ks = 1; a.out_is = (int)ycs;
             a.I = 1024; a.logI = 10;
+            a.in_n = (int)rin; a.in_lf = 1; a.in_li = 0;
+            a.out_n = (int)rout; a.out_lk = 1; a.out_li = 0;
             a.mid = (const float2 *)d.mid.p; a.mid_is = 0;
             a.tw = (const float2 *)d.twV[0].p;
-            int rc = launch_v32(direction == FMB_BACKWARD ? V32_1MC : V32_1M, a, (unsigned)Mf, st);
+            const bool bwd1 = direction == FMB_BACKWARD;
+            unsigned opt = bwd1 ? V32_1KC : V32_1K;
+            if (rin == L && rout == L) opt = bwd1 ? V32_1MC : V32_1M;
+            else if (rin * 2 == L && rout * 2 == L) opt = bwd1 ? V32_1HC : V32_1H;
+            int rc = launch_v32(opt, a, (unsigned)Mf, st);
             if (rc == FMB_OK) done = Mf;
             return rc;
         }
@@ -675,6 +683,7 @@ int launch_v32_a(unsigned opt, const FastArgs<float2> &a, unsigned lines, int sh
 int launch_v32_b(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
 int launch_v32_m(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
 int launch_v32_c(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
+int launch_v32_1(unsigned opt, const FastArgs<float2> &a, unsigned lines, int shape, cudaStream_t st);
 // tile / occupancy instantiation (fft_v32.cuh: launch_v32_variant): FMB_V32_OCC for the strided passes, FMB_V32_MSHAPE for
 // the middle pass of a convolution
 static int launch_v32(unsigned opt, const FastArgs<float2> &a, unsigned lines, cudaStream_t st) {
@@ -684,6 +693,7 @@ static int launch_v32(unsigned opt, const FastArgs<float2> &a, unsigned lines, c
     if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_b(opt, a, lines, shape, st);
     if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_m(opt, a, lines, shape, st);
     if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_c(opt, a, lines, shape, st);
+    if (rc == FMB_ERR_NOTIMPL) rc = launch_v32_1(opt, a, lines, shape, st);
     if (rc == FMB_ERR_NOTIMPL) set_error("V32 path: unknown pass variant %u", opt);
     return rc;
 }

@@ -81,6 +81,7 @@ enum : unsigned {
     FO_IN_HALF = 32768u,     // V32 passes: rows >= L/2 of the input are zero padding (Toeplitz): inputs m >= 16 of a thread are not loaded
     FO_OUT_HALF = 65536u,    // V32 passes: only rows < L/2 of the output are kept: outputs q >= 16 of a thread are not computed
     FO_IN_TWIDDLE = 16384u,  // V32 passes: multiply the INPUT by W_N^{i f} (the four-step twiddle moved out of the previous pass)
+    FO_DYN_LINES = 131072u,  // V32 passes on contiguous lines: the line stride comes from in_is / out_is (else the fixed 1024)
 };
 
 template <typename C> __device__ __forceinline__ C ld_cg(const C *p) { return __ldcg(p); }

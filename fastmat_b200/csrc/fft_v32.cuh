@@ -275,7 +275,8 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
     v32_pos<LOAD_T, LOGT>(tid, jb, t);
     {
         const unsigned i = i0 + t;
-        const C *src = a.in + (long long)col * a.in_cs + (LOAD_T ? (int)i + jb * 1024 : (int)i * 1024 + jb);
+        const C *src = a.in + (long long)col * a.in_cs +
+                       (LOAD_T ? (int)i + jb * 1024 : ((OPT & FO_DYN_LINES) ? (int)i * a.in_is + jb : (int)i * 1024 + jb));
         constexpr int fstep = 32 * 1024;
 #ifdef FMB_PLAIN_BUTTERFLIES
         V32Chain h;
@@ -390,7 +391,8 @@ __global__ void __launch_bounds__(32 << LOGT, MINB) v32_pass_kernel(const __grid
     // last stage output -> global: four-step twiddle W^{i k}, conj, mask, post-multiply
     auto final_store = [&](int jb_, int t_) {
         const unsigned i = i0 + t_;
-        C *dst = a.out + (long long)col * a.out_cs + (STORE_T ? (int)i + jb_ * 1024 : (int)i * 1024 + jb_);
+        C *dst = a.out + (long long)col * a.out_cs +
+                 (STORE_T ? (int)i + jb_ * 1024 : ((OPT & FO_DYN_LINES) ? (int)i * a.out_is + jb_ : (int)i * 1024 + jb_));
         constexpr int kstep = 32 * 1024;
         V32Chain hst;
         if (OPT & FO_TWIDDLE) hst = v32_chain_init(a, i, jb_);
@@ -533,8 +535,13 @@ constexpr unsigned V32_K_A = FO_LOAD_T | FO_STORE_T | FO_OUT_MASK;              
 constexpr unsigned V32_K_AC = V32_K_A | FO_IN_CONJ;
 constexpr unsigned V32_K_B = FO_OUT_MASK;                                        // Kron: over i2 (contiguous)
 constexpr unsigned V32_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
-constexpr unsigned V32_1M = FO_TWO_FFTS | FO_OUT_CONJ;                           // whole Circulant of length 1024 on contiguous columns
-constexpr unsigned V32_1MC = V32_1M | FO_MID_CONJ;                               // (fft_engine.cu: run_single_fast)
+// whole convolutions of FFT length 1024 in one kernel, a line = a column of the operand (fft_engine.cu: run_single_fast):
+constexpr unsigned V32_1M = FO_TWO_FFTS | FO_OUT_CONJ | FO_DYN_LINES;            // Circulant(1024)
+constexpr unsigned V32_1MC = V32_1M | FO_MID_CONJ;
+constexpr unsigned V32_1H = V32_1M | FO_IN_HALF | FO_OUT_HALF;                   // Toeplitz 512 x 512: padding never loaded, dropped rows never stored
+constexpr unsigned V32_1HC = V32_1H | FO_MID_CONJ;
+constexpr unsigned V32_1K = V32_1M | FO_IN_MASK | FO_OUT_MASK;                   // other Toeplitz shapes padded to 1024: masks
+constexpr unsigned V32_1KC = V32_1K | FO_MID_CONJ;
 
 // `shape` selects the tile / occupancy instantiation: strided passes 0 = 8 lines, 2 CTAs per SM (128 registers), 1 = 8 lines,
 // 3 CTAs per SM (80 registers); the middle pass of a convolution (warp-private lines, no CTA barrier) additionally
@@ -546,8 +553,10 @@ template <unsigned OPT, int LOGT, int MINB> int launch_v32_inst(const FastArgs<f
     // per SM (203 KB of shared memory) cost as well, whatever feeds them (profiles/r2_experiments.txt, calls 4, 19, 22, 23)
     static const size_t smem_pad = getenv("FMB_V32_SMEM_PAD") ? (size_t)atol(getenv("FMB_V32_SMEM_PAD")) : 0;
     const size_t smem = (size_t)(1 << LOGT) * V32_RS * sizeof(float2) + smem_pad;
-    if (a.in_fs != (LOAD_T ? 1024 : 1) || a.in_is != (LOAD_T ? 1 : 1024) || a.out_ks != (STORE_T ? 1024 : 1) ||
-        a.out_is != (STORE_T ? 1 : 1024) || a.I != 1024) {
+    constexpr bool DYN = (OPT & FO_DYN_LINES) != 0;
+    static_assert(!DYN || (!LOAD_T && !STORE_T), "a run-time line stride exists on the contiguous sides only");
+    if (a.in_fs != (LOAD_T ? 1024 : 1) || (!DYN && a.in_is != (LOAD_T ? 1 : 1024)) || a.out_ks != (STORE_T ? 1024 : 1) ||
+        (!DYN && a.out_is != (STORE_T ? 1 : 1024)) || a.I != 1024) {
         set_error("V32 pass: arguments do not describe the fixed 1024 x 1024 geometry");
         return FMB_ERR_VALUE;
     }

@@ -8,8 +8,6 @@ int launch_v32_m(unsigned opt, const FastArgs<float2> &a, unsigned lines, int sh
         case V32_BMC: return launch_v32_variant<V32_BMC>(a, lines, shape, st);
         case V32_BM_N: return launch_v32_variant<V32_BM_N>(a, lines, shape, st);
         case V32_BMC_N: return launch_v32_variant<V32_BMC_N>(a, lines, shape, st);
-        case V32_1M: return launch_v32_variant<V32_1M>(a, lines, shape, st);
-        case V32_1MC: return launch_v32_variant<V32_1MC>(a, lines, shape, st);
         default: return FMB_ERR_NOTIMPL;
     }
 }

@@ -926,6 +926,21 @@ def test_single_kernel_fast_path(fm, orc, n):
         xtr = torch.from_numpy(np.ascontiguousarray(xt.astype(dt))).cuda()
         assert np.abs(T.forward(xtr).cpu().numpy() - orc.toeplitz_forward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
         assert np.abs(T.backward(xtr).cpu().numpy() - orc.toeplitz_backward(c[:nt], c[nt:2 * nt - 1], xt)).max() / ntn < tol
+    if n == 1024:
+        # FFT length 1024 runs the 32-value kernel: Circulant above, the pruned Toeplitz (512 x 512) above, and here a
+        # non-square Toeplitz (500 x 512 padded to 1024: masked loads and stores) and a strided column batch
+        vc, vr = c[:500].astype(np.complex64), c[500:1011].astype(np.complex64)
+        T2 = fm.Toeplitz(vc, vr)
+        assert T2.shape == (500, 512)
+        x2 = x[:512]
+        n2 = np.linalg.norm(c) * np.linalg.norm(x2, axis=0).max() * np.log2(n)
+        assert np.abs(T2.forward(dev(x2.astype(np.complex64))).cpu().numpy() - orc.toeplitz_forward(vc, vr, x2)).max() / n2 < TOL64
+        y2 = x[:500]
+        assert np.abs(T2.backward(dev(y2.astype(np.complex64))).cpu().numpy() - orc.toeplitz_backward(vc, vr, y2)).max() / n2 < TOL64
+        C64 = fm.Circulant(c.astype(np.complex64))
+        wide = dev(np.repeat(x.astype(np.complex64), 2, axis=1))
+        ncn = np.linalg.norm(c) * np.linalg.norm(x, axis=0).max() * np.log2(n)
+        assert np.abs(C64.forward(wide[:, ::2]).cpu().numpy() - orc.circulant_forward(c, x)).max() / ncn < TOL64
     # the two routes agree to rounding on the same input (same algorithm, different radix plan)
     import os
     import subprocess
