@@ -557,7 +557,9 @@ print('switches ok', fm.launch_count())
 
 
 @pytest.mark.parametrize('env', [{'FMB_V32T': '1'}, {'FMB_V32T': '0', 'FMB_V32_PRUNE': '0'}, {'FMB_V32_TWM': '1', 'FMB_V32P': '2'},
-                                 {'FMB_V32_OCC': '1', 'FMB_V32_MSHAPE': '3', 'FMB_V32P': '0'}, {'FMB_RM_CHUNK': '0', 'FMB_NO_V32': '1'}],
+                                 {'FMB_V32_OCC': '1', 'FMB_V32_MSHAPE': '3', 'FMB_V32P': '0'}, {'FMB_RM_CHUNK': '0', 'FMB_NO_V32': '1'},
+                                 {'FMB_V32P_INPLACE': '0', 'FMB_V32_INPLACE': '0', 'FMB_FAST_INPLACE': '0'},
+                                 {'FMB_V32P': '0', 'FMB_NO_V32': '1', 'FMB_FAST_INPLACE': '1'}],
                          ids=lambda e: ','.join('%s=%s' % kv for kv in e.items()))
 def test_runtime_switches_keep_results_within_tolerance(fm, env):
     """The A/B switches of the 2^20 kernels (TMA-fed passes, pruning, twiddle placement, tile shapes,
@@ -1016,3 +1018,38 @@ def test_hadamard_unaligned_columns_bit_identical(fm):
         assert xu.stride(0) == 1 and xu.stride(1) == n + 1
         xa = xu.t().contiguous().t()
         assert torch.equal(H.forward(xu), H.forward(xa))
+
+
+_INPLACE_DIGEST = r'''
+import sys, hashlib, numpy as np, torch
+sys.path.insert(0, '.')
+import fastmat_b200 as fm
+g = torch.Generator(device='cuda').manual_seed(21)
+def crandn(n, m): return torch.complex(torch.randn((m, n), device='cuda', generator=g), torch.randn((m, n), device='cuda', generator=g)).t()
+h = hashlib.sha256()
+n, m = 2 ** 20, 13
+x = crandn(n, m)
+c = np.random.default_rng(4).standard_normal(n).astype(np.complex64)
+keep = x.clone()
+for op in (fm.Fourier(n), fm.Kron(fm.Fourier(1024), fm.Fourier(1024)), fm.Circulant(c)):
+    for fn in (op.forward, op.backward):
+        y = fn(x)
+        assert torch.equal(x, keep)                       # the intermediate lives in y, never in x
+        h.update(torch.view_as_real(y).cpu().numpy().tobytes())
+x2 = crandn(2 ** 14, 300)
+h.update(torch.view_as_real(fm.Fourier(2 ** 14).forward(x2)).cpu().numpy().tobytes())
+print('digest', h.hexdigest())
+'''
+
+
+@pytest.mark.gpu
+def test_in_place_intermediate_is_bit_identical_to_ring(fm):
+    """Round 2 keeps the intermediate of plain transforms (persistent 2^20 kernel, 16-value two-pass path) and of the
+    Circulant in y instead of a ring in the workspace (FMB_V32P_INPLACE / FMB_V32_INPLACE / FMB_FAST_INPLACE).  Only the
+    location of the intermediate changes: outputs must be bit-identical to the ring variants, forward and backward, and
+    the input must stay untouched."""
+    a = _run_with_env({}, _INPLACE_DIGEST)
+    b = _run_with_env({'FMB_V32P_INPLACE': '0', 'FMB_V32_INPLACE': '0', 'FMB_FAST_INPLACE': '0'}, _INPLACE_DIGEST)
+    da = [ln for ln in a.splitlines() if ln.startswith('digest')]
+    db = [ln for ln in b.splitlines() if ln.startswith('digest')]
+    assert da and da == db, (da, db)
