@@ -997,7 +997,7 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
     // plain transforms in place: the intermediate is written into y and overwritten there by the second pass - no ring in
     // the L2 working set and no dirty ring lines to write back (FMB_V32P_INPLACE=0: ring)
     static const long inplace_env = env_long("FMB_V32P_INPLACE", 1);
-    const bool inplace = inplace_env && !two_ffts && (const void *)x != (const void *)y && (ycs & 1) == 0 &&
+    const bool inplace = inplace_env && (!two_ffts || rows_out == L) && (const void *)x != (const void *)y && (ycs & 1) == 0 &&
                          (reinterpret_cast<uintptr_t>(y) & 15) == 0 && ycs >= L;
     if (inplace) {
         g.ring = (C *)y; g.ring_cs = ycs; g.slot_stride = (long long)f.slab_cols * ycs;
@@ -1014,7 +1014,7 @@ int ConvEngine::run_v32p(Dev &d, int direction, const void *x, int64_t xcs, void
     {   // pass A: length R1 over n = f*R2 + i; ring[k1*R2 + i] * W^{i k1}    (in place: y[i*R1 + k1])
         FastArgs<C> a = base;
         a.out_cs = L; a.out_ks = R2; a.out_is = 1;
-        if (inplace && kron_a == 0) { a.out_ks = 1; a.out_is = R1; }
+        if (inplace && kron_a == 0 && !two_ffts) { a.out_ks = 1; a.out_is = R1; }
         a.tw = (const C *)d.twV[0].p; a.twS = (const C *)d.twS32[0].p;
         g.pass[0] = a;
     }
