@@ -215,6 +215,8 @@ static int make_kron_fourier(fmb_plan **out, const int64_t *dims, int ndims) {
 // ------------------------------------------------------------------------------------------- Hadamard / Diag / Partial
 struct HadamardPlan : PlanBase {
     int order = 0;
+    // per-slab counters of the persistent order-20 kernel (experiment, FMB_FWHT_PERSIST): at most one slab per column
+    int64_t workspace_bytes(int, int64_t M, int, int) const override { return order == 20 ? (M + 64) * 4 : 0; }
     int info(fmb_plan_info *o) const override {
         memset(o, 0, sizeof(*o));
         o->kind = kind; o->num_rows = num_rows; o->num_cols = num_cols; o->inner_size = num_rows; o->passes_fwd = order > 12 ? 2 : 1;

@@ -318,7 +318,6 @@ __device__ __forceinline__ void fwht_tile(const FwhtFastPass &p, long long tile,
             v[4 * r + 2] = reinterpret_cast<T &>(f.z); v[4 * r + 3] = reinterpret_cast<T &>(f.w);
         }
     } else {
-#pragma unroll
         if (sizeof(T) == 4 && p.pol_in) {
 #pragma unroll
             for (int r = 0; r < 16; ++r) v[r] = fwht_ld_hint(src + (long long)r * step, p.pol_in);
@@ -376,40 +375,36 @@ template <> struct HPm<int32_t> {
 
 __device__ __forceinline__ unsigned fwht_smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 
-template <typename T> __global__ void __launch_bounds__(64, 10) fwht_first12_kernel(const __grid_constant__ FwhtFastPass p) {
-    static_assert(sizeof(T) == 4, "4-byte element types only");
-    typedef typename HPm<T>::S S;
-    extern __shared__ __align__(128) unsigned char fwht12_smem[];
-    T *const buf = reinterpret_cast<T *>(fwht12_smem);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-    const long long tile = blockIdx.x;
-    const long long col = tile >> p.log_tpc, tin = tile & (p.tiles_per_col - 1);
-    const T *gin = (const T *)p.in + col * p.in_cs + (tin << 12);
-    T *gout = (T *)p.out + col * p.out_cs + (tin << 12);
-    const unsigned bar = fwht_smem_u32(fwht12_smem + 16384) + 8u * (unsigned)w;
-    if (lane == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8192u) : "memory");
-        if (p.pol_in)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
-                         ::"r"(fwht_smem_u32(buf + 2048 * w)), "l"(gin + 2048 * w), "r"(8192u), "r"(bar), "l"(p.pol_in) : "memory");
-        else
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         ::"r"(fwht_smem_u32(buf + 2048 * w)), "l"(gin + 2048 * w), "r"(8192u), "r"(bar) : "memory");
-    }
-    __syncwarp();
+// lane 0 of a warp: request this warp's 8 KB half of the line into `half` (completion on `bar`)
+template <typename T> __device__ __forceinline__ void fwht12_issue(const T *gsrc, unsigned half_s, unsigned bar, unsigned long long pol_in) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8192u) : "memory");
+    if (pol_in)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                     ::"r"(half_s), "l"(gsrc), "r"(8192u), "r"(bar), "l"(pol_in) : "memory");
+    else
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(half_s), "l"(gsrc), "r"(8192u), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fwht_mbar_wait(unsigned bar, unsigned parity) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "FWHT12_WAIT_%=:\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
         "@p bra FWHT12_DONE_%=;\n\t"
         "bra FWHT12_WAIT_%=;\n\t"
-        "FWHT12_DONE_%=:\n\t}" ::"r"(bar), "r"(0u), "r"(0x989680u) : "memory");
+        "FWHT12_DONE_%=:\n\t}" ::"r"(bar), "r"(parity), "r"(0x989680u) : "memory");
+}
+
+// the two register sub-stages of one line by 64 threads (tid64): `buf` holds the line (this thread's warp has waited for
+// its half), `group_sync` is a barrier of the 64 threads
+template <typename T, typename Sync>
+__device__ __forceinline__ void fwht12_compute(T *const buf, T *const gout, const int tid64, const int lane, const unsigned long long pol_out,
+                                               Sync group_sync) {
+    typedef typename HPm<T>::S S;
     T v[64];
     // ---- sub-stage 1: own row, skewed chunk order
     const int k = lane & 7;
-    unsigned char *const row = reinterpret_cast<unsigned char *>(buf + 64 * tid);
+    unsigned char *const row = reinterpret_cast<unsigned char *>(buf + 64 * tid64);
     const int kb = k << 4;
 #pragma unroll
     for (int s = 0; s < 16; ++s) {
@@ -451,10 +446,10 @@ template <typename T> __global__ void __launch_bounds__(64, 10) fwht_first12_ker
         q.z = reinterpret_cast<const int &>(v[4 * s + 2]); q.w = reinterpret_cast<const int &>(v[4 * s + 3]);
         *reinterpret_cast<int4 *>(row + ((s << 4) ^ kb)) = q;
     }
-    __syncthreads();
+    group_sync();
     // ---- sub-stage 2: elements tid + 64 j
 #pragma unroll
-    for (int j = 0; j < 64; ++j) v[j] = buf[64 * j + tid];
+    for (int j = 0; j < 64; ++j) v[j] = buf[64 * j + tid64];
 #pragma unroll
     for (int lev = 0; lev < 6; ++lev) {
         const int d = 1 << lev;
@@ -462,13 +457,33 @@ template <typename T> __global__ void __launch_bounds__(64, 10) fwht_first12_ker
         for (int r = 0; r < 64; ++r)
             if ((r & d) == 0) { const T a = v[r], b = v[r | d]; v[r] = HOps<T>::add(a, b); v[r | d] = HOps<T>::sub(a, b); }
     }
-    if (p.pol_out) {
+    if (pol_out) {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) fwht_st_hint(gout + 64 * j + tid, v[j], p.pol_out);
+        for (int j = 0; j < 64; ++j) fwht_st_hint(gout + 64 * j + tid64, v[j], pol_out);
     } else {
 #pragma unroll
-        for (int j = 0; j < 64; ++j) gout[64 * j + tid] = v[j];
+        for (int j = 0; j < 64; ++j) gout[64 * j + tid64] = v[j];
     }
+}
+
+template <typename T> __global__ void __launch_bounds__(64, 10) fwht_first12_kernel(const __grid_constant__ FwhtFastPass p) {
+    static_assert(sizeof(T) == 4, "4-byte element types only");
+    extern __shared__ __align__(128) unsigned char fwht12_smem[];
+    T *const buf = reinterpret_cast<T *>(fwht12_smem);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const long long tile = blockIdx.x;
+    const long long col = tile >> p.log_tpc, tin = tile & (p.tiles_per_col - 1);
+    const T *gin = (const T *)p.in + col * p.in_cs + (tin << 12);
+    T *gout = (T *)p.out + col * p.out_cs + (tin << 12);
+    const unsigned bar = fwht_smem_u32(fwht12_smem + 16384) + 8u * (unsigned)w;
+    if (lane == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fwht12_issue<T>(gin + 2048 * w, fwht_smem_u32(buf + 2048 * w), bar, p.pol_in);
+    }
+    __syncwarp();
+    fwht_mbar_wait(bar, 0u);
+    fwht12_compute<T>(buf, gout, tid, lane, p.pol_out, []() { __syncthreads(); });
 }
 
 template <typename T> struct FwhtHas12 { static constexpr bool value = false; };
@@ -528,33 +543,123 @@ template <typename T> __device__ __forceinline__ FwhtVec4<T> fwht_ld128(const Fw
     return r;
 }
 
+template <typename T> __device__ __forceinline__ FwhtVec4<T> fwht_ld128_cg(const FwhtVec4<T> *p) {      // L2 only: written by other SMs in this launch
+    int4 q;
+    asm volatile("ld.global.cg.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(q.x), "=r"(q.y), "=r"(q.z), "=r"(q.w) : "l"(p) : "memory");
+    FwhtVec4<T> r;
+    r.x = reinterpret_cast<const T &>(q.x); r.y = reinterpret_cast<const T &>(q.y); r.z = reinterpret_cast<const T &>(q.z); r.w = reinterpret_cast<const T &>(q.w);
+    return r;
+}
+
+// one tile (256 mids x 64 lines) by 256 threads; gin / gout point at (mid 0, line 4 * l16) of the tile
+template <typename T, bool CG, int LV = 16>
+__device__ __forceinline__ void fwht_s8_tile(const T *gin, T *gout, FwhtVec4<T> *const sm, const int tid, const long long step) {
+    typedef FwhtVec4<T> V;
+    const int l16 = tid & (LV - 1), q = tid / LV;
+    V v[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const V *src = reinterpret_cast<const V *>(gin + (long long)(16 * q + r) * step);
+        v[r] = CG ? fwht_ld128_cg(src) : fwht_ld128(src);
+    }
+    fwht16x4<T>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) sm[(16 * q + r) * LV + l16] = v[r];
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = sm[(q + 16 * r) * LV + l16];
+    fwht16x4<T>(v);
+#pragma unroll
+    for (int r = 0; r < 16; ++r) *reinterpret_cast<V *>(gout + (long long)(q + 16 * r) * step) = v[r];
+}
+
 template <typename T, int LOGSTEP> __global__ void __launch_bounds__(256, 3) fwht_strided8_kernel(const __grid_constant__ FwhtFastPass p) {
     static_assert(sizeof(T) == 4, "4-byte element types only");
     typedef FwhtVec4<T> V;
     extern __shared__ __align__(16) unsigned char fwht_s8_smem[];
     V *const sm = reinterpret_cast<V *>(fwht_s8_smem);            // [256 mids][16 vectors]
-    const int tid = threadIdx.x, l16 = tid & 15, q = tid >> 4;
+    const int tid = threadIdx.x, l16 = tid & 15;
     const int s = LOGSTEP >= 0 ? LOGSTEP : p.s;
     const long long tile = blockIdx.x;
     const long long col = tile >> p.log_tpc, tin = tile & (p.tiles_per_col - 1);
     const int log_lo = s - 6;                                     // tiles along the low index: 2^s / 64
     const long long hi = tin >> log_lo, lo0 = (tin & (((long long)1 << log_lo) - 1)) << 6;
     const long long base = (hi << (s + 8)) + lo0 + 4 * l16;
-    const long long step = (long long)1 << s;
-    const T *gin = (const T *)p.in + col * p.in_cs + base;
-    T *gout = (T *)p.out + col * p.out_cs + base;
-    V v[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = fwht_ld128(reinterpret_cast<const V *>(gin + (long long)(16 * q + r) * step));
-    fwht16x4<T>(v);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) sm[(16 * q + r) * 16 + l16] = v[r];
+    fwht_s8_tile<T, false>((const T *)p.in + col * p.in_cs + base, (T *)p.out + col * p.out_cs + base, sm, tid, (long long)1 << s);
+}
+
+// ------------------------------------------------------------------------------------------- order 20, persistent (experiment)
+// Both passes of the order-20 transform of 4-byte types in ONE cooperative launch (FMB_FWHT_PERSIST=1): CTA c walks the
+// item list c, c + G, ...; step t of the list interleaves the first-pass items of column slab t (4 lines = 64 KB each, one
+// 64-thread group per line) with the second-pass tiles of slab t - D (64 KB each), so every CTA alternates between the
+// passes and a waiting second pass throttles the first (tools/ubench_pipe_persistent.cu: without that back-pressure the
+// first pass runs away and the intermediate is gone from L2).  A second-pass tile waits on a per-slab counter that every
+// finished first-pass item bumps (release / acquire at gpu scope).  All CTAs are co-resident (cooperative launch) and take
+// their items in increasing order, so the wait cannot deadlock.
+struct FwhtPersistArgs {
+    const void *x; void *y;
+    long long xcs, ycs;
+    unsigned *done;                 // [nslabs], zeroed before the launch
+    int ncols, slab_cols, nslabs, dist;
+    unsigned per_step;              // 2 * 64 * slab_cols
+    unsigned total_items;
+};
+
+__device__ __forceinline__ unsigned fwht_ld_acquire(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <typename T, int NT> __global__ void __launch_bounds__(NT, NT == 256 ? 2 : 5) fwht_persist20_kernel(const __grid_constant__ FwhtPersistArgs a) {
+    static_assert(sizeof(T) == 4, "4-byte element types only");
+    extern __shared__ __align__(128) unsigned char fwhtp_smem[];
+    constexpr int NG = NT / 64, LV = NT / 16;                                      // lines per first-pass item; vectors per mid of a strided tile
+    constexpr int LOG_I1 = NT == 256 ? 6 : 7, LOG_I2 = NT == 256 ? 6 : 7;          // items per column and pass: 256 / NG, 1024 / (4 LV)
+    T *const buf = reinterpret_cast<T *>(fwhtp_smem);                              // NG lines / one strided tile (NT * 256 bytes)
+    const unsigned bars = fwht_smem_u32(fwhtp_smem + NT * 256);                    // one mbarrier per warp
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, grp = tid >> 6, tid64 = tid & 63, w = warp & 1;
+    const unsigned bar = bars + 8u * (unsigned)warp;
+    if (lane == 0) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(1u) : "memory");
+    if (tid == 0) asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     __syncthreads();
-#pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = sm[(q + 16 * r) * 16 + l16];
-    fwht16x4<T>(v);
-#pragma unroll
-    for (int r = 0; r < 16; ++r) *reinterpret_cast<V *>(gout + (long long)(q + 16 * r) * step) = v[r];
+    unsigned n1 = 0;                                                               // first-pass items done by this CTA (barrier phase)
+    for (unsigned item = blockIdx.x; item < a.total_items; item += gridDim.x) {
+        const unsigned step = item / a.per_step, r = item - step * a.per_step, pass2 = r & 1u, idx = r >> 1;
+        const int slab = pass2 ? (int)step - a.dist : (int)step;
+        if (slab < 0 || slab >= a.nslabs) continue;
+        const int col = slab * a.slab_cols + (int)(idx >> LOG_I1);
+        if (col >= a.ncols) continue;
+        __syncthreads();                                                           // everybody is done with the buffer of the previous item
+        if (!pass2) {
+            const long long line = NG * (long long)(idx & ((1u << LOG_I1) - 1u)) + grp;   // line of 4096 elements inside the column
+            const T *gin = (const T *)a.x + (long long)col * a.xcs + (line << 12);
+            T *gout = (T *)a.y + (long long)col * a.ycs + (line << 12);
+            T *const lbuf = buf + 4096 * grp;
+            if (lane == 0) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic accesses of the last item before the bulk copy
+                fwht12_issue<T>(gin + 2048 * w, fwht_smem_u32(lbuf + 2048 * w), bar, 0ull);
+            }
+            __syncwarp();
+            fwht_mbar_wait(bar, n1 & 1u);
+            ++n1;
+            fwht12_compute<T>(lbuf, gout, tid64, lane, 0ull, [grp]() { asm volatile("bar.sync %0, 64;" ::"r"(grp + 1) : "memory"); });
+            __syncthreads();                                                       // all stores of the item issued
+            if (tid == 0) {
+                __threadfence();
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(a.done + slab), "r"(1u) : "memory");
+            }
+        } else {
+            const int cols_here = min(a.slab_cols, a.ncols - slab * a.slab_cols);
+            const unsigned need = (unsigned)cols_here << LOG_I1;
+            if (tid == 0) while (fwht_ld_acquire(a.done + slab) < need) __nanosleep(100);
+            __syncthreads();
+            const unsigned tin = idx & ((1u << LOG_I2) - 1u);                      // tile in the column (order 20: one hi value): 4 LV lines each
+            const long long base = (long long)tin * (4 * LV) + 4 * (tid & (LV - 1));
+            T *g = (T *)a.y + (long long)col * a.ycs + base;
+            fwht_s8_tile<T, true, LV>(g, g, reinterpret_cast<FwhtVec4<T> *>(buf), tid, (long long)1 << 12);
+        }
+    }
 }
 
 template <typename T> static int fwht_strided8_launch(const FwhtFastPass &p, long long ncols, cudaStream_t st, bool &done) {
@@ -617,8 +722,62 @@ template <typename T> static int fwht_fast_launch(const FwhtFastPass &p, unsigne
     return FMB_OK;
 }
 
+
+template <typename T>
+static int fwht_persist20_launch(const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes, cudaStream_t st, bool &done) {
+    done = false;
+    if constexpr (FwhtHas12<T>::value) {
+        static const long slab_env = getenv("FMB_FWHT_PERSIST_SLAB") ? atol(getenv("FMB_FWHT_PERSIST_SLAB")) : 2;
+        static const long dist_env = getenv("FMB_FWHT_PERSIST_DIST") ? atol(getenv("FMB_FWHT_PERSIST_DIST")) : 2;
+        static const long ctas_env = getenv("FMB_FWHT_PERSIST_CTAS") ? atol(getenv("FMB_FWHT_PERSIST_CTAS")) : 8;
+        if ((reinterpret_cast<unsigned long long>(x) & 15ull) || (reinterpret_cast<unsigned long long>(y) & 15ull) || (xcs & 3) || (ycs & 3)) return FMB_OK;
+        if (x == (const void *)y || M >= ((int64_t)1 << 24)) return FMB_OK;
+        FwhtPersistArgs a;
+        memset(&a, 0, sizeof(a));
+        a.x = x; a.y = y; a.xcs = xcs; a.ycs = ycs;
+        a.ncols = (int)M; a.slab_cols = (int)std::max<long>(1, std::min<long>(slab_env, 16));
+        a.nslabs = (int)((M + a.slab_cols - 1) / a.slab_cols);
+        a.dist = (int)std::max<long>(1, dist_env);
+        static const long nt_env = getenv("FMB_FWHT_PERSIST_NT") ? atol(getenv("FMB_FWHT_PERSIST_NT")) : 256;
+        const int NT = nt_env == 128 ? 128 : 256;
+        a.per_step = 2u * (NT == 256 ? 64u : 128u) * (unsigned)a.slab_cols;
+        const int64_t total = ((int64_t)a.nslabs + a.dist) * a.per_step;
+        if (total >= ((int64_t)1 << 32) || ws == nullptr || ws_bytes < (int64_t)a.nslabs * 4) return FMB_OK;
+        a.total_items = (unsigned)total;
+        a.done = (unsigned *)ws;
+        const size_t smem = (size_t)NT * 256 + 64;
+        const void *kern = NT == 256 ? (const void *)fwht_persist20_kernel<T, 256> : (const void *)fwht_persist20_kernel<T, 128>;
+        static int per_sm = 0;
+        if (!per_sm) {
+            FMB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            FMB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
+            if (per_sm < 1) per_sm = -1;
+        }
+        if (per_sm < 1) return FMB_OK;
+        int grid = device_props().sm_count * (int)std::min<long>(per_sm, std::max<long>(1, ctas_env));
+        if ((grid & 1) == 0) --grid;                                 // odd: every CTA alternates between the two passes
+        if ((unsigned)grid > a.total_items) grid = (int)a.total_items | 1;
+        FMB_CUDA_OK(cudaMemsetAsync(ws, 0, (size_t)a.nslabs * 4, st));
+        void *args[1] = {&a};
+        const cudaError_t e = cudaLaunchCooperativeKernel(kern, dim3((unsigned)grid), dim3((unsigned)NT), args, smem, st);
+        if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorLaunchOutOfResources) { (void)cudaGetLastError(); return FMB_OK; }
+        if (e != cudaSuccess) { set_error("persistent FWHT launch failed: %s", cudaGetErrorString(e)); return FMB_ERR_CUDA; }
+        g_launches.fetch_add(1);
+        done = true;
+    }
+    return FMB_OK;
+}
+
 template <typename T>
 static int fwht_fast(int order, const void *x, int64_t xcs, void *y, int64_t ycs, int64_t M, void *ws, int64_t ws_bytes, cudaStream_t st) {
+    {
+        static const long persist = getenv("FMB_FWHT_PERSIST") ? atol(getenv("FMB_FWHT_PERSIST")) : 0;
+        if (persist && order == 20 && M >= 16) {
+            bool done = false;
+            int rc = fwht_persist20_launch<T>(x, xcs, y, ycs, M, ws, ws_bytes, st, done);
+            if (rc || done) return rc;
+        }
+    }
     // bit ranges per pass: a contiguous first pass of up to 12 bits, then strided passes of 4..8 bits
     std::vector<int> bits;
     if (order <= 12) bits.push_back(order);

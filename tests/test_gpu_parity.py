@@ -1053,3 +1053,35 @@ def test_in_place_intermediate_is_bit_identical_to_ring(fm):
     da = [ln for ln in a.splitlines() if ln.startswith('digest')]
     db = [ln for ln in b.splitlines() if ln.startswith('digest')]
     assert da and da == db, (da, db)
+
+
+_FWHT_DIGEST = r'''
+import sys, hashlib, torch
+sys.path.insert(0, '.')
+import fastmat_b200 as fm
+g = torch.Generator(device='cuda').manual_seed(31)
+H = fm.Hadamard(20)
+h = hashlib.sha256()
+for m in (37, 16, 130):
+    xf = torch.randn((m, 2 ** 20), device='cuda', generator=g).t()
+    xi = torch.randint(-2 ** 31, 2 ** 31 - 1, (m, 2 ** 20), dtype=torch.int32, device='cuda', generator=g).t()
+    for x in (xf, xi):
+        keep = x.clone()
+        y = H.forward(x)
+        assert torch.equal(x, keep)
+        h.update(y.cpu().numpy().tobytes())
+print('digest', h.hexdigest(), fm.launch_count())
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('env', [{'FMB_FWHT_PERSIST': '1'}, {'FMB_FWHT_PERSIST': '1', 'FMB_FWHT_PERSIST_NT': '128', 'FMB_FWHT_PERSIST_SLAB': '1', 'FMB_FWHT_PERSIST_DIST': '4'},
+                                 {'FMB_FWHT_NO12': '1', 'FMB_FWHT_NO_S8': '1'}, {'FMB_FWHT_PIPE_STREAMS': '1'}],
+                         ids=lambda e: ','.join('%s=%s' % kv for kv in e.items()))
+def test_fwht_schedules_are_bit_identical(fm, env):
+    """Order-20 FWHT, float32 and int32, ragged column counts: the persistent cooperative kernel (opt-in experiment, both
+    CTA shapes), the round-1 pass kernels and the single-stream schedule all produce the bits of the default path (same
+    butterflies in the same order; only the schedule and the data movement differ)."""
+    a = [ln.split()[1] for ln in _run_with_env({}, _FWHT_DIGEST).splitlines() if ln.startswith('digest')]
+    b = [ln.split()[1] for ln in _run_with_env(env, _FWHT_DIGEST).splitlines() if ln.startswith('digest')]
+    assert a and a == b, (a, b)
