@@ -91,7 +91,7 @@ class Circulant(Matrix):
         if self._nested is not None:
             return self._nested.forward(x) if direction == FORWARD else self._nested.backward(x)
         ft_out = fft_out_type(_t.getFusedType(x.dtype), self._fusedType)
-        return plan_apply(self._plan, direction, fft_in_prepare(x, ft_out), self._numRows, ft_out)
+        return plan_apply(self._plan, direction, fft_in_prepare(x, ft_out, self._plan), self._numRows, ft_out)
 
     def _forward(self, x):
         return self._apply(FORWARD, x)

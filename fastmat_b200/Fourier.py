@@ -38,7 +38,7 @@ class Fourier(Matrix):
 
     def _apply(self, direction, x):
         ft_out = fft_out_type(_t.getFusedType(x.dtype), self._fusedType)
-        return plan_apply(self._plan, direction, fft_in_prepare(x, ft_out), self._order, ft_out)
+        return plan_apply(self._plan, direction, fft_in_prepare(x, ft_out, self._plan), self._order, ft_out)
 
     def _forward(self, x):
         return self._apply(FORWARD, x)

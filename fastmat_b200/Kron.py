@@ -64,13 +64,13 @@ class Kron(Matrix):
     def _forward(self, x):
         if self._plan is not None:
             ft_out = _t.promoteTypes(x.dtype, _t.TYPE_COMPLEX64)
-            return plan_apply(self._plan, FORWARD, fft_in_prepare(x, ft_out), self._numRows, ft_out)
+            return plan_apply(self._plan, FORWARD, fft_in_prepare(x, ft_out, self._plan), self._numRows, ft_out)
         return self._chain(x, False)
 
     def _backward(self, x):
         if self._plan is not None:
             ft_out = _t.promoteTypes(x.dtype, _t.TYPE_COMPLEX64)
-            return plan_apply(self._plan, BACKWARD, fft_in_prepare(x, ft_out), self._numRows, ft_out)
+            return plan_apply(self._plan, BACKWARD, fft_in_prepare(x, ft_out, self._plan), self._numRows, ft_out)
         return self._chain(x, True)
 
     # analytic overrides: fastmat/Kron.pyx:155-183

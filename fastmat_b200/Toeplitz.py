@@ -158,7 +158,7 @@ class Toeplitz(Matrix):
             return self._nested.forward(x) if direction == FORWARD else self._nested.backward(x)
         ft_out = fft_out_type(_t.getFusedType(x.dtype), self._fusedType)
         rows_out = self._numRows if direction == FORWARD else self._numCols
-        return plan_apply(self._plan, direction, fft_in_prepare(x, ft_out), rows_out, ft_out)
+        return plan_apply(self._plan, direction, fft_in_prepare(x, ft_out, self._plan), rows_out, ft_out)
 
     def _forward(self, x):
         return self._apply(FORWARD, x)

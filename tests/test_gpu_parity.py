@@ -1085,3 +1085,40 @@ def test_fwht_schedules_are_bit_identical(fm, env):
     a = [ln.split()[1] for ln in _run_with_env({}, _FWHT_DIGEST).splitlines() if ln.startswith('digest')]
     b = [ln.split()[1] for ln in _run_with_env(env, _FWHT_DIGEST).splitlines() if ln.startswith('digest')]
     assert a and a == b, (a, b)
+
+
+_REAL_CHECK = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import fastmat_b200 as fm
+from oracle import fastmat_oracle as orc
+rng = np.random.default_rng(12)
+for n, m in ((2 ** 14, 21), (1024, 70), (2 ** 20, 3)):
+    for dt, tol in ((np.float32, 1e-5), (np.float64, 1e-12)):
+        x = rng.standard_normal((n, m)).astype(dt)
+        c = rng.standard_normal(n).astype(dt)
+        xd = torch.from_numpy(np.asfortranarray(x).T.copy()).cuda().t()
+        nx = np.linalg.norm(x, axis=0).max() * np.log2(n)
+        y = fm.Fourier(n).forward(xd)
+        assert y.dtype == (torch.complex64 if dt == np.float32 else torch.complex128)
+        assert np.abs(y.cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        C = fm.Circulant(c)
+        yc = C.forward(xd).cpu().numpy()
+        assert np.abs(yc - orc.circulant_forward(c, x)).max() / (np.linalg.norm(c) * nx) < tol
+        yb = C.backward(xd).cpu().numpy()
+        assert np.abs(yb - orc.circulant_backward(c, x)).max() / (np.linalg.norm(c) * nx) < tol
+        nt = n // 2
+        T = fm.Toeplitz(c[:nt], c[nt:2 * nt - 1])
+        yt = T.forward(xd[:nt]).cpu().numpy()
+        assert np.abs(yt - orc.toeplitz_forward(c[:nt], c[nt:2 * nt - 1], x[:nt])).max() / (np.linalg.norm(c) * nx) < tol
+print('real ok')
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('cast', ['1', '0'])
+def test_real_operands_on_fft_operators(fm, cast):
+    """float32 / float64 operands of Fourier / Circulant / Toeplitz at power-of-two sizes: widened to complex in front of
+    the specialised kernels (default) or read directly by the generic real-input kernels (FMB_REAL_CAST=0); both against
+    the oracle (fastmat returns complex results for real operands of these operators)."""
+    assert 'real ok' in _run_with_env({'FMB_REAL_CAST': cast}, _REAL_CHECK)
