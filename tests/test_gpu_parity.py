@@ -1122,3 +1122,44 @@ def test_real_operands_on_fft_operators(fm, cast):
     the specialised kernels (default) or read directly by the generic real-input kernels (FMB_REAL_CAST=0); both against
     the oracle (fastmat returns complex results for real operands of these operators)."""
     assert 'real ok' in _run_with_env({'FMB_REAL_CAST': cast}, _REAL_CHECK)
+
+
+@pytest.mark.gpu
+def test_strided_output_through_the_c_abi_keeps_the_gaps(fm):
+    """The in-place variants use y itself as the intermediate.  Through the C-ABI y may be a strided view (column stride
+    larger than the row count): only rows [0, n) of every column may be written, the padding between the columns must keep
+    its bytes, and the result must equal the contiguous call.  Fourier / Kron / Circulant 2^20 (persistent kernel and
+    per-pass route), Fourier 2^14 (16-value path), Circulant 1024 (single kernel), Hadamard order 20 (in-place passes)."""
+    from fastmat_b200 import _lib
+    from fastmat_b200.Matrix import _stream_ptr
+    from fastmat_b200.core import types as T
+    rng = np.random.default_rng(17)
+    g = torch.Generator(device='cuda').manual_seed(17)
+
+    def crandn(n, m):
+        return torch.complex(torch.randn((m, n), device='cuda', generator=g), torch.randn((m, n), device='cuda', generator=g)).t()
+
+    def cvec(n):
+        return (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+
+    cases = [(fm.Fourier(2 ** 20), crandn(2 ** 20, 9)), (fm.Kron(fm.Fourier(1024), fm.Fourier(1024)), crandn(2 ** 20, 9)),
+             (fm.Circulant(cvec(2 ** 20)), crandn(2 ** 20, 13)), (fm.Fourier(2 ** 14), crandn(2 ** 14, 300)),
+             (fm.Circulant(cvec(1024)), crandn(1024, 100)), (fm.Hadamard(20), torch.randn((27, 2 ** 20), device='cuda', generator=g).t())]
+    for op, x in cases:
+        n, m = x.shape
+        pad = 64
+        ref = op.forward(x)
+        sentinel = 12345.0
+        buf = torch.full((m, n + pad), sentinel, dtype=ref.dtype, device='cuda')
+        y = buf[:, :n].t()                                 # column-major view, column stride n + pad
+        assert y.stride(0) == 1 and y.stride(1) == n + pad
+        ft = T.getFusedType(x.dtype)
+        fo = T.getFusedType(ref.dtype)
+        plan = op._plan
+        wsb = _lib.lib.fmb_plan_workspace_bytes(plan.handle, _lib.FORWARD, m, ft, fo)
+        ws = torch.empty(max(wsb, 1), dtype=torch.uint8, device='cuda')
+        _lib.check(_lib.lib.fmb_plan_apply(plan.handle, _lib.FORWARD, x.data_ptr(), x.stride(0), x.stride(1), y.data_ptr(), y.stride(0),
+                                           y.stride(1), m, ft, fo, ws.data_ptr(), wsb, _stream_ptr(x.device)))
+        torch.cuda.synchronize()
+        assert torch.equal(y, ref), repr(op)
+        assert bool((buf[:, n:] == sentinel).all()), repr(op)
