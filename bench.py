@@ -390,7 +390,7 @@ def run_ours(args):
 
     # per-kernel share of a step and DRAM traffic come from the ncu launch list of this command committed under profiles/;
     # they are quoted only if that list was captured on the kernel sources being timed now (source hash), else null + why
-    traffic, kernels, dominant, prof_note = None, None, None, None
+    traffic, kernels, dominant, prof_note, traffic_conc, conc_note = None, None, None, None, None, None
     shash = source_hash()
     try:
         with open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')) as f:
@@ -400,6 +400,8 @@ def run_ours(args):
         else:
             if cols == COLS:
                 traffic = tj['dram_bytes_per_step']
+                traffic_conc = tj.get('dram_bytes_per_step_concurrent')
+                conc_note = tj.get('concurrent_note')
             kernels = {k: {'share_of_step_time': v['share_of_step_time'], 'avg_us_under_ncu': v['avg_us']}
                        for k, v in tj['kernels'].items() if v['share_of_step_time'] > 0.01}
             dominant = tj.get('dominant_kernel')
@@ -577,7 +579,8 @@ def run_ours(args):
             'e2e': e2e,
             'gpu_launches': int(launches),
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                         'traffic': traffic, 'peak_source': peak_src,
+                         'traffic': traffic, 'traffic_under_concurrency': traffic_conc, 'traffic_under_concurrency_note': conc_note,
+                         'peak_source': peak_src,
                          'algorithmic_bytes_per_step': alg_bytes,
                          'note': ('operator level: algorithmic bytes of one step (2 x 8 B x N per column, SURVEY 8d) / CUDA-event '
                                   'time of the step on the caller stream; one step = %d launches (3 passes per slab of %d columns, '

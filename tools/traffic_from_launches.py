@@ -2,7 +2,10 @@
 
     ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv \
         --log-file launches.csv python bench.py --steps 2 --warmup 1 --quick --no-e2e --no-cpu
-    python tools/traffic_from_launches.py launches.csv profiles/r2_traffic.json <launches of EACH pass kernel per step>
+    python tools/traffic_from_launches.py launches.csv profiles/r2_traffic.json <launches of EACH pass kernel per step> [range_replay.txt]
+
+The optional fourth argument is the output of `ncu --replay-mode range` of ONE whole apply (tools/r2_profile.sh): its DRAM
+bytes are those of the step under its real concurrency (the launch list serialises the kernels, which keeps every slab in L2).
 
 ncu serialises the launches and flushes caches between them, so absolute times are cold-cache; what bench.py quotes
 from here is each kernel's SHARE of a step and the DRAM bytes per step.
@@ -52,5 +55,17 @@ out['dram_bytes_per_step'] = sum((v['rd'] + v['wr']) / len(v['ids']) * per_step 
 out['algorithmic_bytes_per_step'] = 2 * 8 * N * COLS
 out['traffic_over_algorithmic'] = out['dram_bytes_per_step'] / out['algorithmic_bytes_per_step']
 out['dominant_kernel'] = max(ours, key=lambda k: ours[k]['ns'])
+if len(sys.argv) > 4:
+    rd = wr = None
+    for ln in open(sys.argv[4]):
+        t = ln.split()
+        if len(t) >= 3 and t[0] == 'dram__bytes_read.sum':
+            rd = float(t[-1]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[t[1]]
+        if len(t) >= 3 and t[0] == 'dram__bytes_write.sum':
+            wr = float(t[-1]) * {'Gbyte': 1e9, 'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0}[t[1]]
+    if rd is not None and wr is not None:
+        out['dram_bytes_per_step_concurrent'] = rd + wr
+        out['concurrent_note'] = ('ncu --replay-mode range of one whole apply (all slabs, internal streams): %.2f GB read + %.2f GB written = '
+                                  '%.2fx the algorithmic bytes' % (rd / 1e9, wr / 1e9, (rd + wr) / out['algorithmic_bytes_per_step']))
 json.dump(out, open(dst, 'w'), indent=1)
 print(json.dumps({k: out[k] for k in ('dram_bytes_per_step', 'traffic_over_algorithmic', 'dominant_kernel')}))
