@@ -467,6 +467,10 @@ def run_ours(args):
 
         def rec(name, fn, ncols, bytes_per_col, k=None, w=3, sustain=None):
             try:
+                # every row starts from an idle GPU (the rows before it leave the board power-capped): ms_per_step is the
+                # figure of the operator timed alone, sustained_ms_per_step the back-to-back steady state next to it
+                torch.cuda.synchronize()
+                time.sleep(args.extras_idle)
                 ms_, ms_s = timed(fn, k or k2, w, sus if sustain is None else sustain)
                 r = {'ms_per_step': ms_, 'columns': ncols, 'columns_per_s': ncols / (ms_ * 1e-3),
                      'hbm_gbs': bytes_per_col * ncols / (ms_ * 1e-3) / 1e9,
@@ -622,6 +626,7 @@ def main():
     ap.add_argument('--sustain', type=float, default=2.0, help='seconds of back-to-back steps for the sustained figure (0: off)')
     ap.add_argument('--cpu-cols', type=int, default=16, dest='cpu_cols')
     ap.add_argument('--c5-cols', type=int, default=128, dest='c5_cols', help='right-hand sides per GPU of the config-5 solver rows')
+    ap.add_argument('--extras-idle', type=float, default=1.0, dest='extras_idle', help='idle seconds before each extras row')
     ap.add_argument('--quick', action='store_true', help='headline only (no extras)')
     ap.add_argument('--no-e2e', action='store_true', dest='no_e2e')
     ap.add_argument('--no-cpu', action='store_true', dest='no_cpu')
