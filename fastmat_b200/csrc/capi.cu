@@ -136,8 +136,14 @@ static int make_fourier(fmb_plan **out, int64_t order, int optimize, int max_sta
         double rhs = (double)rhs_f + 2.0 * (double)order;
         p->bluestein_ref = ((double)fft_complexity(order) < rhs) ? 0 : padded;
     }
+    // directly transformable lengths that are not powers of two would run the run-time-radix kernels (3 - 7 % of the
+    // roofline); from 4097 on the chirp-z transform over the next power of two (specialised kernels) is 1.5 - 3x faster
+    // (FMB_POW2_PAD=0: direct).  `bluestein_ref` above keeps reporting the reference's own decision.
+    static const long pow2_pad = getenv("FMB_POW2_PAD") ? atol(getenv("FMB_POW2_PAD")) : 1;
     FftShape shape;
-    if (plan_shape(order, shape)) rc = p->eng.init(order, order, order, false);
+    bool direct = plan_shape(order, shape);
+    if (direct && pow2_pad && (order & (order - 1)) != 0 && order > 4096 && next_pow2(2 * order - 1) <= ((int64_t)1 << 24)) direct = false;
+    if (direct) rc = p->eng.init(order, order, order, false);
     else rc = setup_bluestein(p->eng, order);
     if (rc) return rc;
     *out = reinterpret_cast<fmb_plan *>(static_cast<PlanBase *>(p.release()));
@@ -158,6 +164,19 @@ static int make_conv(fmb_plan **out, int kind, const std::vector<cd> &gen, int64
     return FMB_OK;
 }
 
+// The reference pads to the length its CPU cost model likes best (2^a 3^b 5^c ..., cmath.pyx:88-153); any length that
+// embeds the operator gives the same result.  On this device the power-of-two lengths run compile-time specialised kernels
+// at 25 - 90 % of the HBM roofline and every other length the run-time-radix kernels at 3 - 7 %, so a non-power-of-two
+// choice is replaced by the next power of two that still embeds the operator (`need`), unless that is out of the
+// specialised range (FMB_POW2_PAD=0: keep the reference's choice).  The planner functions themselves stay bit-identical.
+static int64_t prefer_pow2_length(int64_t chosen, int64_t /*valid_exact*/, int64_t need) {
+    static const long on = getenv("FMB_POW2_PAD") ? atol(getenv("FMB_POW2_PAD")) : 1;
+    if (!on || chosen < 2 || (chosen & (chosen - 1)) == 0) return chosen;
+    const int64_t p2 = next_pow2(need);
+    if (p2 < 64 || p2 > ((int64_t)1 << 24)) return chosen;
+    return p2;
+}
+
 static int make_circulant(fmb_plan **out, const void *c_host, int64_t n, int optimize, int max_stage) {
     if (n < 1 || !c_host) { set_error("Column-definition tensor must be at least 1D."); return FMB_ERR_VALUE; }
     int rc = require_device();
@@ -170,6 +189,7 @@ static int make_circulant(fmb_plan **out, const void *c_host, int64_t n, int opt
     }
     FftShape shape;
     if (!plan_shape(L, shape) || (L != n && L < 2 * n - 1)) L = std::max<int64_t>(2, next_pow2(2 * n - 1));
+    L = prefer_pow2_length(L, L == n ? n : 2 * n - 1, 2 * n - 1);
     std::vector<cd> gen((size_t)L, cd(0, 0));
     for (int64_t i = 0; i < n; ++i) gen[(size_t)i] = c[i];
     if (L != n)
@@ -193,6 +213,7 @@ static int make_toeplitz(fmb_plan **out, const void *vc_host, int64_t n, const v
     }
     FftShape shape;
     if (!plan_shape(L, shape) || L < d) L = std::max<int64_t>(2, next_pow2(d));
+    L = prefer_pow2_length(L, d, d);
     std::vector<cd> gen((size_t)L, cd(0, 0));                           // [vecC, zeros, vecR]  (_preProcSlice :357-366)
     for (int64_t i = 0; i < n; ++i) gen[(size_t)i] = vc[i];
     for (int64_t i = 0; i < m1; ++i) gen[(size_t)(L - m1 + i)] = vr[i];

@@ -1163,3 +1163,45 @@ def test_strided_output_through_the_c_abi_keeps_the_gaps(fm):
         torch.cuda.synchronize()
         assert torch.equal(y, ref), repr(op)
         assert bool((buf[:, n:] == sentinel).all()), repr(op)
+
+
+_PAD_CHECK = r'''
+import sys, numpy as np, torch
+sys.path.insert(0, '.')
+import fastmat_b200 as fm
+from oracle import fastmat_oracle as orc
+rng = np.random.default_rng(23)
+def dev(a): return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
+inner = []
+for n in (41, 100, 1000, 3000, 6144, 5000, 41000):
+    for dt, tol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
+        x = (rng.standard_normal((n, 9)) + 1j * rng.standard_normal((n, 9))).astype(dt)
+        c = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(dt)
+        nx = np.linalg.norm(x, axis=0).max() * np.log2(n)
+        C = fm.Circulant(c)
+        assert np.abs(C.forward(dev(x)).cpu().numpy() - orc.circulant_forward(c, x)).max() / (np.linalg.norm(c) * nx) < tol
+        assert np.abs(C.backward(dev(x)).cpu().numpy() - orc.circulant_backward(c, x)).max() / (np.linalg.norm(c) * nx) < tol
+        vr = c[1:][::-1].copy()
+        T = fm.Toeplitz(c, vr)
+        assert np.abs(T.forward(dev(x)).cpu().numpy() - orc.toeplitz_forward(c, vr, x)).max() / (np.linalg.norm(c) * nx) < tol
+        assert np.abs(T.backward(dev(x)).cpu().numpy() - orc.toeplitz_backward(c, vr, x)).max() / (np.linalg.norm(c) * nx) < tol
+        F = fm.Fourier(n)
+        assert np.abs(F.forward(dev(x)).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        assert np.abs(F.backward(dev(x)).cpu().numpy() - orc.fourier_backward(x)).max() / nx < tol
+    inner.append((int(C._plan.info.inner_size), int(T._plan.info.inner_size), int(F._plan.info.inner_size)))
+print('pad ok', inner)
+'''
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('pad', ['1', '0'])
+def test_padded_length_policy(fm, pad):
+    """Lengths that are not powers of two: by default Circulant / Toeplitz pad to the next power of two that embeds them
+    and Fourier orders above 4096 run as chirp-z transforms over a power of two (specialised kernels); FMB_POW2_PAD=0 keeps
+    the reference planner's choice (2^a 3^b 5^c lengths, run-time-radix kernels).  Same operator either way: both against
+    the oracle, both precisions, forward and backward."""
+    out = _run_with_env({'FMB_POW2_PAD': pad}, _PAD_CHECK)
+    assert 'pad ok' in out
+    inner = eval(out.split('pad ok', 1)[1].strip().splitlines()[0])
+    pow2 = [all(v & (v - 1) == 0 for v in t[:2]) for t in inner]
+    assert all(pow2) if pad == '1' else not all(pow2)
