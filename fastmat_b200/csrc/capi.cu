@@ -82,6 +82,10 @@ static size_t out_csize(int dt_out) { return dt_out == FMB_COMPLEX64 ? sizeof(fl
 // ------------------------------------------------------------------------------------------- engine-backed plans
 struct EnginePlan : PlanBase {
     ConvEngine eng;
+    // Fourier orders run as chirp-z over a power of two although they are directly transformable (make_fourier) keep the
+    // direct engine too: complex128 has no specialised single kernel at a padded length of 4096 and is better served by it
+    std::unique_ptr<ConvEngine> direct;
+    bool use_direct(int dt_out) const { return direct && dt_out == FMB_COMPLEX128 && eng.L == 4096; }
     int64_t bluestein_ref = 0;        // the reference's _numL decision, for the record
     int info(fmb_plan_info *o) const override {
         memset(o, 0, sizeof(*o));
@@ -94,9 +98,12 @@ struct EnginePlan : PlanBase {
         }
         return FMB_OK;
     }
-    int64_t workspace_bytes(int, int64_t M, int, int dt_out) const override { return eng.workspace_bytes(M, out_csize(dt_out)); }
+    int64_t workspace_bytes(int, int64_t M, int, int dt_out) const override {
+        return use_direct(dt_out) ? direct->workspace_bytes(M, out_csize(dt_out)) : eng.workspace_bytes(M, out_csize(dt_out));
+    }
     int apply(int direction, const void *x, int64_t xrs, int64_t xcs, void *y, int64_t yrs, int64_t ycs, int64_t M, int dt_in,
               int dt_out, void *ws, int64_t wsb, cudaStream_t st) const override {
+        if (use_direct(dt_out)) return direct->run(direction, x, xrs, xcs, y, yrs, ycs, M, dt_in, dt_out, ws, wsb, st);
         return eng.run(direction, x, xrs, xcs, y, yrs, ycs, M, dt_in, dt_out, ws, wsb, st);
     }
 };
@@ -137,14 +144,21 @@ static int make_fourier(fmb_plan **out, int64_t order, int optimize, int max_sta
         p->bluestein_ref = ((double)fft_complexity(order) < rhs) ? 0 : padded;
     }
     // directly transformable lengths that are not powers of two would run the run-time-radix kernels (3 - 7 % of the
-    // roofline); from 4097 on the chirp-z transform over the next power of two (specialised kernels) is 1.5 - 3x faster
-    // (FMB_POW2_PAD=0: direct).  `bluestein_ref` above keeps reporting the reference's own decision.
+    // roofline); the chirp-z transform over the next power of two (specialised kernels: one launch up to a padded length
+    // of 4096, the two-pass path above) is 1.5 - 6x faster from order 33 on (FMB_POW2_PAD=0: direct).  `bluestein_ref`
+    // above keeps reporting the reference's own decision.
     static const long pow2_pad = getenv("FMB_POW2_PAD") ? atol(getenv("FMB_POW2_PAD")) : 1;
     FftShape shape;
     bool direct = plan_shape(order, shape);
-    if (direct && pow2_pad && (order & (order - 1)) != 0 && order > 4096 && next_pow2(2 * order - 1) <= ((int64_t)1 << 24)) direct = false;
+    if (direct && pow2_pad && (order & (order - 1)) != 0 && order > 32 && next_pow2(2 * order - 1) <= ((int64_t)1 << 24)) direct = false;
     if (direct) rc = p->eng.init(order, order, order, false);
-    else rc = setup_bluestein(p->eng, order);
+    else {
+        rc = setup_bluestein(p->eng, order);
+        if (rc == FMB_OK && p->eng.L == 4096 && plan_shape(order, shape)) {
+            p->direct.reset(new ConvEngine());
+            rc = p->direct->init(order, order, order, false);
+        }
+    }
     if (rc) return rc;
     *out = reinterpret_cast<fmb_plan *>(static_cast<PlanBase *>(p.release()));
     return FMB_OK;

@@ -508,8 +508,9 @@ int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xr
     static const long off = env_long("FMB_NO_FAST", 0), off1 = env_long("FMB_NO_FAST1", 0), no_v32 = env_long("FMB_NO_V32", 0);
     const int l = ilog2_host(L);
     if (off || off1 || !shape.pow2 || shape.npass != 1 || !fast_has((const C *)nullptr, l)) return FMB_OK;
-    if (!pre.empty() || !post.empty() || (two_ffts && mid.empty())) return FMB_OK;
-    if constexpr (sizeof(C) == sizeof(float2)) {
+    const bool chirp = !pre.empty() || !post.empty();                  // chirp-z (Bluestein): pre- and post-multiply around the convolution
+    if ((chirp && (pre.empty() || post.empty() || !two_ffts)) || (two_ffts && mid.empty())) return FMB_OK;
+    if constexpr (sizeof(C) == sizeof(float2)) if (!chirp) {
         // Convolutions of FFT length 1024 (Circulant(1024); Toeplitz padded to 1024) on column-major batches: the middle
         // pass of the 2^20 transforms IS this operator (FFT -> spectrum -> FFT on contiguous, warp-private lines, 32 values
         // per thread, fused twiddle butterflies) with the same spectrum for every line and the column stride as line stride
@@ -561,7 +562,9 @@ int ConvEngine::run_single_fast(Dev &d, int direction, const void *x, int64_t xr
     a.out_n = (int)(bwd ? n_in : n_out); a.out_lk = 1; a.out_li = 0;
     a.mid = (const C *)d.mid.p; a.mid_is = 0;
     a.tw = (const C *)d.twF[0].p;
-    const unsigned opt = (two_ffts ? (bwd ? FV_1_MC_ : FV_1_M_) : (bwd ? FV_1_FC_ : FV_K_B_)) | (rm ? (FO_LOAD_T | FO_STORE_T) : 0u);
+    if (chirp) { a.pre = (const C *)(bwd ? d.post.p : d.pre.p); a.post = (const C *)(bwd ? d.pre.p : d.post.p); }   // the adjoint swaps and conjugates them
+    const unsigned opt = (two_ffts ? (bwd ? FV_1_MC_ : FV_1_M_) : (bwd ? FV_1_FC_ : FV_K_B_)) | (rm ? (FO_LOAD_T | FO_STORE_T) : 0u) |
+                         (chirp ? (FO_PRE | FO_POST | (bwd ? (FO_PRE_CONJ | FO_POST_CONJ) : 0u)) : 0u);
     int rc = fast_launch(l, opt, a, (unsigned)(Mf >> lt), st);
     if (rc == FMB_OK) done = Mf;
     return rc;

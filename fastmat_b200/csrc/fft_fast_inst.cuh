@@ -25,10 +25,14 @@ constexpr unsigned FV_K_BC = FO_OUT_MASK | FO_OUT_CONJ;
 constexpr unsigned FV_1_FC = FO_IN_CONJ | FO_OUT_CONJ | FO_OUT_MASK;                  // backward Fourier (forward: FV_K_B)
 constexpr unsigned FV_1_M = FO_TWO_FFTS | FO_IN_MASK | FO_OUT_CONJ | FO_OUT_MASK;     // Circulant / Toeplitz on chip
 constexpr unsigned FV_1_MC = FV_1_M | FO_MID_CONJ;
+constexpr unsigned FV_1_MP = FV_1_M | FO_PRE | FO_POST;                                // ... chirp-z on chip: pre- and post-multiply
+constexpr unsigned FV_1_MPC = FV_1_MP | FO_MID_CONJ | FO_PRE_CONJ | FO_POST_CONJ;
 constexpr unsigned FV_1T = FO_LOAD_T | FO_STORE_T;                                    // the same for row-major operands: the
 constexpr unsigned FV_1T_FC = FV_1_FC | FV_1T;                                        // T columns of a tile are contiguous
 constexpr unsigned FV_1T_M = FV_1_M | FV_1T;                                          // (forward Fourier: FV_B_F)
 constexpr unsigned FV_1T_MC = FV_1_MC | FV_1T;
+constexpr unsigned FV_1T_MP = FV_1_MP | FV_1T;
+constexpr unsigned FV_1T_MPC = FV_1_MPC | FV_1T;
 
 template <typename C, int LOGR, unsigned OPT>
 int launch_fast_variant(const FastArgs<C> &a, unsigned tiles, cudaStream_t st) {
@@ -68,6 +72,10 @@ template <typename C, int LOGR> int launch_fast_logr(unsigned opt, const FastArg
         case FV_1T_FC: return launch_fast_variant<C, LOGR, FV_1T_FC>(a, tiles, st);
         case FV_1T_M: return launch_fast_variant<C, LOGR, FV_1T_M>(a, tiles, st);
         case FV_1T_MC: return launch_fast_variant<C, LOGR, FV_1T_MC>(a, tiles, st);
+        case FV_1_MP: return launch_fast_variant<C, LOGR, FV_1_MP>(a, tiles, st);
+        case FV_1_MPC: return launch_fast_variant<C, LOGR, FV_1_MPC>(a, tiles, st);
+        case FV_1T_MP: return launch_fast_variant<C, LOGR, FV_1T_MP>(a, tiles, st);
+        case FV_1T_MPC: return launch_fast_variant<C, LOGR, FV_1T_MPC>(a, tiles, st);
         default: set_error("fast path: unknown pass variant %u", opt); return FMB_ERR_NOTIMPL;
     }
 }

@@ -1173,7 +1173,7 @@ from oracle import fastmat_oracle as orc
 rng = np.random.default_rng(23)
 def dev(a): return torch.from_numpy(np.ascontiguousarray(a.T)).cuda().t()
 inner = []
-for n in (41, 100, 1000, 3000, 6144, 5000, 41000):
+for n in (41, 100, 1000, 1500, 3000, 6144, 5000, 41000):
     for dt, tol in ((np.complex64, 1e-5), (np.complex128, 1e-12)):
         x = (rng.standard_normal((n, 9)) + 1j * rng.standard_normal((n, 9))).astype(dt)
         c = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(dt)
@@ -1188,6 +1188,10 @@ for n in (41, 100, 1000, 3000, 6144, 5000, 41000):
         F = fm.Fourier(n)
         assert np.abs(F.forward(dev(x)).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
         assert np.abs(F.backward(dev(x)).cpu().numpy() - orc.fourier_backward(x)).max() / nx < tol
+        xr = torch.from_numpy(np.ascontiguousarray(x)).cuda()          # row-major operand
+        assert np.abs(F.forward(xr).cpu().numpy() - orc.fourier_forward(x)).max() / nx < tol
+        xw = (rng.standard_normal((n, 70)) + 1j * rng.standard_normal((n, 70))).astype(dt)   # whole tiles + ragged tail
+        assert np.abs(F.forward(dev(xw)).cpu().numpy() - orc.fourier_forward(xw)).max() / (np.linalg.norm(xw, axis=0).max() * np.log2(n)) < tol
     inner.append((int(C._plan.info.inner_size), int(T._plan.info.inner_size), int(F._plan.info.inner_size)))
 print('pad ok', inner)
 '''

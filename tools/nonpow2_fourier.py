@@ -1,7 +1,7 @@
 import sys, numpy as np, torch
 sys.path.insert(0, '/root/repo')
 import fastmat_b200 as fm
-for n, cols in ((6144, 1024), (110592, 256), (5000, 1024), (786432, 32), (12288, 1024)):
+for n, cols in ((100, 65536), (1000, 16384), (1500, 8192), (3000, 4096), (6144, 1024), (110592, 256), (5000, 1024), (786432, 32), (12288, 1024)):
     x = torch.view_as_complex(torch.randn((cols, n, 2), dtype=torch.float32, device='cuda')).t()
     F = fm.Fourier(n)
     ref = torch.fft.fft(x[:, :2].to(torch.complex128), dim=0)
